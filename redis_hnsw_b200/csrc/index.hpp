@@ -1,0 +1,99 @@
+// The index object behind the C ABI (host side).  Device layout: see common.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "launch.cuh"
+
+namespace hnsw {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launches;
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct HostRows {
+  std::vector<uint32_t> adj0, ovf0, adjU, ovfU, pool;
+};
+
+struct Index {
+  // parameters (core.rs:303-312)
+  int device = 0;
+  uint32_t dim = 0, m = 0, m_max = 0, m_max_0 = 0, ef_construction = 0;
+  double level_mult = 0;
+  int dist_mode = 0, vecw = 1, kind = 0;
+  int num_sms = 148;
+  size_t max_smem = 0;
+
+  // device state
+  Graph g{};
+  uint64_t cap_nodes = 0, cap_upper = 0;
+  cudaStream_t stream = nullptr;
+
+  // host mirrors (core.rs:313-317)
+  uint64_t n_ids = 0, node_count = 0, upper_used = 0;
+  uint32_t pool_used = 0;
+  int32_t entry = -1, max_layer = 0, device_error = 0;
+  std::vector<int32_t> h_level;
+  std::vector<uint32_t> h_upper_base;
+  std::vector<uint32_t> touched;
+  uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+  uint64_t build_stats[4] = {0, 0, 0, 0};
+
+  // options / adaptive state
+  uint32_t opt_vis_slots = 0;
+  int opt_ctas_per_sm = 0, opt_block = 0;
+  uint32_t opt_build_batch = 0;
+  uint32_t auto_vis_ef = 0, auto_vis_slots = 0;  // adaptive visited-table size for the last-used ef
+  uint32_t* h_retry_seen = nullptr;              // pinned: retry count of the previous async search
+
+  // scratch
+  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage;
+
+  ~Index();
+  int use_device();
+  int ensure_nodes(uint64_t n);
+  int ensure_upper(uint64_t rows);
+  int ensure_pool(uint64_t rows);
+  int ensure_scratch(Scratch& s, size_t bytes);
+  int push_meta();
+  int pull_meta();
+  int upload_vectors(const float* host, uint64_t first_row, uint64_t rows);
+  int download_vectors(float* host, uint64_t first_row, uint64_t rows);
+  int load_graph(uint64_t n, const float* vectors, const int32_t* levels, const uint64_t* row_offs,
+                 const uint32_t* nbrs, int64_t entry, int32_t max_layer);
+  int snapshot_rows(HostRows& h);
+  void row_list(const HostRows& h, uint32_t node, uint32_t level, std::vector<uint32_t>& out) const;
+
+  // search (search_host.cu)
+  int search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_sims,
+                    uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s);
+  int search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uint32_t* ids, float* sims, uint32_t* counts,
+                  uint32_t* stats);
+  int search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
+                        uint32_t* n_out);
+  uint32_t pick_vis_slots(uint32_t ef);
+};
+
+}  // namespace hnsw
+
+// the opaque handle of include/hnsw_b200.h
+struct hnsw_index {
+  hnsw::Index impl;
+};
+
+#define IDX_OR_FAIL(idx)                                                \
+  if (!(idx)) return hnsw::fail(HNSW_ERR_INVALID, "null index handle"); \
+  hnsw::Index& ix = (idx)->impl;                                        \
+  {                                                                     \
+    int rc_ = ix.use_device();                                          \
+    if (rc_) return rc_;                                                \
+  }

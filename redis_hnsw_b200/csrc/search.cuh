@@ -1,0 +1,466 @@
+// search_layer / search_knn for one warp per query (reference: src/hnsw/core.rs:607-675, 865-892).
+//
+// Formulation.  The reference keeps two heaps, `c` (candidates, unbounded) and `w` (results, <= ef).  Every
+// member of `w` is also pushed to `c`, an element leaves `w` only by being the worst when a better one arrives,
+// and the loop stops when the nearest element of `c` is farther than the worst of `w` (core.rs:635).  An element
+// evicted from `w` is never expanded afterwards (everything left in `w` is nearer), so the state is exactly:
+// the ef best nodes seen so far, each with an "expanded" flag; expand the nearest unexpanded one until none is
+// left.  A candidate's neighbours can be evaluated as a batch because the final content of `w` after the batch
+// is the top-ef of (w ∪ batch) whatever the order (core.rs:657-664) — as long as no two sims tie.
+//
+// State per warp: a sorted candidate list distributed over registers (entry e lives in lane e % 32, register
+// e / 32), an exact visited hash set in shared memory (or global memory for the large-ef / retry pass), and the
+// query chunks in registers (or shared memory for the generic / scalar distance modes).
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "distance.cuh"
+
+namespace hnsw {
+
+struct Counters {
+  uint32_t n_dist, n_adj, n_hops;
+};
+
+// ---------------------------------------------------------------- sorted candidate list in registers
+
+template <int EFR>
+struct CandList {
+  float sim[EFR];
+  uint32_t id[EFR];  // kEmpty = unused; bit 31 = expanded
+  int len;           // warp-uniform
+  float worst;       // warp-uniform; sim of entry ef-1 once len == ef, else -inf
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) sim[r] = -CUDART_INF_F, id[r] = kEmpty;
+    len = 0;
+    worst = -CUDART_INF_F;
+  }
+
+  __device__ __forceinline__ bool admits(float s, int ef) const { return len < ef || s > worst; }  // core.rs:657
+
+  // Insert (s, nid) keeping descending order (new entry goes after equal sims).  Caller checked admits().
+  __device__ __forceinline__ void insert(float s, uint32_t nid, int ef, int lane) {
+    int p = 0;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) p += __popc(__ballot_sync(kFull, id[r] != kEmpty && sim[r] >= s));
+#pragma unroll
+    for (int r = EFR - 1; r >= 0; --r) {
+      if (r * 32 + 31 < p) continue;  // warp-uniform: nothing at or after p in this register
+      float us = __shfl_up_sync(kFull, sim[r], 1);
+      uint32_t ui = __shfl_up_sync(kFull, id[r], 1);
+      if (r > 0) {
+        float cs = __shfl_sync(kFull, sim[r - 1], 31);
+        uint32_t ci = __shfl_sync(kFull, id[r - 1], 31);
+        if (lane == 0) us = cs, ui = ci;
+      }
+      int e = r * 32 + lane;
+      if (e > p) sim[r] = us, id[r] = ui;
+      else if (e == p) sim[r] = s, id[r] = nid;
+    }
+    if (len < ef) ++len;
+    // drop what fell past ef (only possible when ef is not the full register capacity)
+    if (ef < EFR * 32) {
+#pragma unroll
+      for (int r = 0; r < EFR; ++r)
+        if (r * 32 + lane >= ef) sim[r] = -CUDART_INF_F, id[r] = kEmpty;
+    }
+    if (len == ef) {
+      float v = 0.f;
+      int wr = (ef - 1) >> 5;
+#pragma unroll
+      for (int r = 0; r < EFR; ++r)
+        if (r == wr) v = sim[r];
+      worst = __shfl_sync(kFull, v, (ef - 1) & 31);
+    }
+  }
+
+  // index of the nearest unexpanded entry, or -1
+  __device__ __forceinline__ int first_unexpanded() const {
+    int pos = -1;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) {
+      uint32_t b = __ballot_sync(kFull, id[r] != kEmpty && !(id[r] & kExpanded));
+      if (pos < 0 && b) pos = r * 32 + __ffs(b) - 1;
+    }
+    return pos;
+  }
+
+  // read entry `pos` (warp-uniform) and optionally mark it expanded
+  __device__ __forceinline__ void get(int pos, int lane, bool mark, uint32_t& nid, float& s) {
+    uint32_t vi = kEmpty;
+    float vs = 0.f;
+    int rr = pos >> 5, l = pos & 31;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r)
+      if (r == rr) {
+        vi = id[r], vs = sim[r];
+        if (mark && lane == l) id[r] |= kExpanded;
+      }
+    nid = __shfl_sync(kFull, vi, l) & ~kExpanded;
+    s = __shfl_sync(kFull, vs, l);
+  }
+};
+
+// ---------------------------------------------------------------- exact visited set (open addressing)
+
+struct Visited {
+  uint32_t* tab;    // slots (shared or global memory), kEmpty = free
+  uint32_t mask;    // slots - 1
+  uint32_t count;   // warp-uniform number of stored ids
+  uint32_t limit;   // abort threshold (load factor 3/4)
+  int shift;        // 32 - log2(slots)
+};
+
+__device__ __forceinline__ void visited_clear(Visited& v, int lane) {
+  uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+  uint4* t = reinterpret_cast<uint4*>(v.tab);
+  for (uint32_t i = lane; i < (v.mask + 1) / 4; i += 32) t[i] = e;
+  v.count = 0;
+  __syncwarp();
+}
+
+// Warp-collective test-and-insert: lanes with `active` offer distinct ids; returns true where the id was new.
+// Lanes race for free slots with plain stores and re-read after a warp barrier; the loser moves on.
+__device__ __forceinline__ bool visited_insert(Visited& v, uint32_t nid, bool active) {
+  bool pending = active, is_new = false;
+  uint32_t slot = (nid * 2654435761u) >> v.shift;
+  while (__any_sync(kFull, pending)) {
+    uint32_t cur = pending ? v.tab[slot] : 0u;
+    bool try_write = pending && cur == kEmpty;
+    if (pending && cur == nid) pending = false;  // seen before
+    if (try_write) v.tab[slot] = nid;
+    __syncwarp();
+    if (try_write) {
+      if (v.tab[slot] == nid) is_new = true, pending = false;
+      else slot = (slot + 1) & v.mask;
+    } else if (pending) {
+      slot = (slot + 1) & v.mask;
+    }
+    __syncwarp();
+  }
+  v.count += __popc(__ballot_sync(kFull, is_new));
+  return is_new;
+}
+
+// ---------------------------------------------------------------- distance providers
+
+// dim = 32*C known at compile time: query chunks in registers, rows fetched with one V-wide load per group.
+template <int C_>
+struct DistReg {
+  static constexpr int C = C_;
+  static constexpr int U = (C <= 4) ? 4 : ((C <= 8) ? 2 : 1);  // rows in flight per lane
+  static constexpr bool kNeedsSmemQuery = false;
+  float q[C];
+  __device__ __forceinline__ void load_query(const float* __restrict__ qn, float*, uint32_t, int lane) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) q[c] = qn[32 * c + lane];
+  }
+  __device__ __forceinline__ float one(const Graph& g, uint32_t nid, int lane) const {
+    RowRegs<C> r;
+    load_row_regs<C>(g.vecs + (size_t)nid * (32 * C), lane, r);
+    return warp_hsum_avx_order(lane_partial<C>(q, r));
+  }
+  // sims of the neighbours flagged in `mask` (lane j holds neighbour id `nb`); lane j gets its own
+  __device__ __forceinline__ float batch(const Graph& g, uint32_t nb, uint32_t mask, int lane) const {
+    float mine = -CUDART_INF_F;
+    while (mask) {
+      int j[U];
+      RowRegs<C> rr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        j[u] = mask ? (__ffs(mask) - 1) : -1;
+        mask &= mask - 1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j[u] >= 0) {
+          uint32_t nid = __shfl_sync(kFull, nb, j[u]);
+          load_row_regs<C>(g.vecs + (size_t)nid * (32 * C), lane, rr[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j[u] >= 0) {
+          float s = warp_hsum_avx_order(lane_partial<C>(q, rr[u]));
+          if (lane == j[u]) mine = s;
+        }
+    }
+    return mine;
+  }
+};
+
+// dim % 32 == 0, any size: permuted query in shared memory.
+struct DistGeneric {
+  static constexpr bool kNeedsSmemQuery = true;
+  const float* qs;
+  uint32_t C;
+  int V;
+  __device__ __forceinline__ void load_query(const float* __restrict__ qn, float* smem_q, uint32_t dim, int lane) {
+    C = dim / 32;
+    V = dist_vec_width(dim);
+    for (uint32_t i = lane; i < dim; i += 32) smem_q[permuted_pos(i, V)] = qn[i];
+    qs = smem_q;
+    __syncwarp();
+  }
+  __device__ __forceinline__ float one(const Graph& g, uint32_t nid, int lane) const {
+    return warp_hsum_avx_order(lane_partial_generic(qs, g.vecs + (size_t)nid * (32 * C), C, V, lane));
+  }
+  __device__ __forceinline__ float batch(const Graph& g, uint32_t nb, uint32_t mask, int lane) const {
+    float mine = -CUDART_INF_F;
+    while (mask) {
+      int j0 = __ffs(mask) - 1;
+      mask &= mask - 1;
+      int j1 = mask ? (__ffs(mask) - 1) : -1;
+      mask &= mask - 1;
+      uint32_t n0 = __shfl_sync(kFull, nb, j0);
+      float p0 = lane_partial_generic(qs, g.vecs + (size_t)n0 * (32 * C), C, V, lane);
+      float p1 = 0.f;
+      if (j1 >= 0) {
+        uint32_t n1 = __shfl_sync(kFull, nb, j1);
+        p1 = lane_partial_generic(qs, g.vecs + (size_t)n1 * (32 * C), C, V, lane);
+      }
+      float s0 = warp_hsum_avx_order(p0);
+      if (lane == j0) mine = s0;
+      if (j1 >= 0) {
+        float s1 = warp_hsum_avx_order(p1);
+        if (lane == j1) mine = s1;
+      }
+    }
+    return mine;
+  }
+};
+
+// dim % 32 != 0: reference scalar fold, one lane per row, natural-order query in shared memory.
+struct DistScalar {
+  static constexpr bool kNeedsSmemQuery = true;
+  const float* qs;
+  uint32_t dim;
+  __device__ __forceinline__ void load_query(const float* __restrict__ qn, float* smem_q, uint32_t d, int lane) {
+    dim = d;
+    for (uint32_t i = lane; i < d; i += 32) smem_q[i] = qn[i];
+    qs = smem_q;
+    __syncwarp();
+  }
+  __device__ __forceinline__ float one(const Graph& g, uint32_t nid, int) const {
+    return scalar_sim(qs, g.vecs + (size_t)nid * dim, dim);  // every lane computes the same value
+  }
+  __device__ __forceinline__ float batch(const Graph& g, uint32_t nb, uint32_t mask, int lane) const {
+    if ((mask >> lane) & 1u) return scalar_sim(qs, g.vecs + (size_t)nb * dim, dim);
+    return -CUDART_INF_F;
+  }
+};
+
+// ---------------------------------------------------------------- search_layer (core.rs:607-675)
+
+// Evaluate one chunk of <= 32 neighbour ids (lane j holds nb or kEmpty) against the list.
+// Returns false if the visited table passed its load limit (caller aborts and retries with a larger table).
+template <int EFR, class Dist>
+__device__ __forceinline__ bool expand_chunk(const Graph& g, const Dist& dist, uint32_t nb, int ef, CandList<EFR>& L,
+                                             Visited& vis, Counters& cnt, int lane) {
+  bool valid = nb != kEmpty;
+  uint32_t vmask = __ballot_sync(kFull, valid);
+  if (!vmask) return true;
+  cnt.n_adj += __popc(vmask);                                  // core.rs:646
+  bool is_new = visited_insert(vis, nb, valid);                // core.rs:648-649
+  uint32_t newmask = __ballot_sync(kFull, is_new);
+  if (vis.count > vis.limit) return false;
+  if (!newmask) return true;
+  cnt.n_dist += __popc(newmask);
+  float mine = dist.batch(g, nb, newmask, lane);               // core.rs:652-656
+  uint32_t cand = __ballot_sync(kFull, is_new && L.admits(mine, ef));
+  while (cand) {                                               // list order, threshold re-read (core.rs:651,657)
+    int j = __ffs(cand) - 1;
+    cand &= cand - 1;
+    float s = __shfl_sync(kFull, mine, j);
+    uint32_t nid = __shfl_sync(kFull, nb, j);
+    if (L.admits(s, ef)) L.insert(s, nid, ef, lane);           // core.rs:658-664
+  }
+  return true;
+}
+
+// Greedy best-first search of one level from entry point `ep`.  On return L holds the result set `w`
+// nearest-first.  `expanded_out` (optional, global memory) receives the ids whose adjacency rows were read.
+template <int EFR, class Dist>
+__device__ __forceinline__ bool search_layer(const Graph& g, const Dist& dist, uint32_t ep, int ef, uint32_t level,
+                                             CandList<EFR>& L, Visited& vis, Counters& cnt, int lane,
+                                             uint32_t* expanded_out = nullptr, uint32_t expanded_cap = 0,
+                                             uint32_t* n_expanded = nullptr) {
+  visited_clear(vis, lane);
+  visited_insert(vis, ep, lane == 0);                          // core.rs:617
+  float s_ep = dist.one(g, ep, lane);                          // core.rs:621
+  cnt.n_dist += 1;
+  L.init();
+  L.insert(s_ep, ep, ef, lane);                                // core.rs:627-628
+  uint32_t nexp = 0;
+  for (;;) {
+    int pos = L.first_unexpanded();                            // core.rs:631-638
+    if (pos < 0) break;
+    uint32_t cid;
+    float cs;
+    L.get(pos, lane, true, cid, cs);
+    cnt.n_hops += 1;
+    if (expanded_out) {
+      if (nexp < expanded_cap && lane == 0) expanded_out[nexp] = cid;
+      ++nexp;
+    }
+    uint32_t* ovf;
+    const uint32_t* row = row_ptr(g, cid, level, &ovf);        // core.rs:642-645
+    if (!row) continue;
+    uint32_t link = *ovf;
+    bool more = true;
+    for (uint32_t w = 0; w < g.W / 32 && more; ++w) {
+      uint32_t nb = row[w * 32 + lane];
+      more = __shfl_sync(kFull, nb, 31) != kEmpty;             // rows are compact: an empty tail ends the list
+      if (!expand_chunk<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, lane)) return false;
+    }
+    while (more && link != kEmpty) {                           // overflow rows (degree is unbounded)
+      uint32_t nb = g.pool[(size_t)link * 32 + lane];
+      link = __shfl_sync(kFull, nb, 31);
+      if (lane == 31) nb = kEmpty;
+      if (!expand_chunk<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, lane)) return false;
+    }
+  }
+  if (n_expanded) *n_expanded = nexp;
+  return true;
+}
+
+// ---------------------------------------------------------------- search_knn kernel (core.rs:477-486, 865-892)
+
+struct SearchArgs {
+  const float* queries;   // [nq][dim] natural order
+  uint32_t nq;
+  uint32_t k;
+  uint32_t ef;
+  uint32_t* ids;          // [nq][k]
+  float* sims;            // [nq][k]
+  uint32_t* counts;       // [nq]
+  uint32_t* stats;        // [nq][4] or null
+  uint32_t* work_counter; // dynamic query scheduler
+  uint32_t* retry_list;   // queries whose visited table overflowed in the shared-memory pass
+  uint32_t* retry_count;
+  uint32_t vis_slots;     // per-warp visited slots (power of two)
+  uint32_t* vis_global;   // [warps][vis_slots] when the table lives in global memory
+  int retry_pass;         // 1: take query indices from retry_list
+};
+
+template <int EFR, class Dist, bool VIS_SMEM>
+__global__ void __launch_bounds__(256) search_knn_kernel(Graph g, SearchArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+
+  Visited vis;
+  vis.mask = a.vis_slots - 1;
+  vis.shift = 32 - (31 - __clz(a.vis_slots));
+  vis.limit = a.vis_slots - a.vis_slots / 4;
+  float* smem_q = nullptr;
+  if (VIS_SMEM) {
+    vis.tab = smem + (size_t)warp * a.vis_slots;
+    if (Dist::kNeedsSmemQuery) smem_q = reinterpret_cast<float*>(smem + (size_t)warps * a.vis_slots) + (size_t)warp * g.dim;
+  } else {
+    vis.tab = a.vis_global + ((size_t)blockIdx.x * warps + warp) * a.vis_slots;
+    if (Dist::kNeedsSmemQuery) smem_q = reinterpret_cast<float*>(smem) + (size_t)warp * g.dim;
+  }
+
+  const uint32_t total = a.retry_pass ? *a.retry_count : a.nq;
+  Dist dist;
+  CandList<EFR> L;
+
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(a.work_counter, 1u);
+    wi = __shfl_sync(kFull, wi, 0);
+    if (wi >= total) break;
+    const uint32_t qi = a.retry_pass ? a.retry_list[wi] : wi;
+
+    Counters cnt = {0, 0, 0};
+    dist.load_query(a.queries + (size_t)qi * g.dim, smem_q, g.dim, lane);
+    const int32_t entry = g.meta[kMetaEntry];
+    bool ok = true;
+    uint32_t n_out = 0;
+    if (entry >= 0) {                                          // core.rs:481-483 (empty index -> no results)
+      uint32_t ep = (uint32_t)entry;
+      // core.rs:869-876: ef = 1 on the upper levels, taking the nearest as the next entry point; `ef` on level 0
+      for (int lc = g.meta[kMetaMaxLayer]; lc >= 0 && ok; --lc) {
+        ok = search_layer<EFR, Dist>(g, dist, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, vis, cnt, lane);
+        float s;
+        if (ok && lc > 0) L.get(0, lane, false, ep, s);
+      }
+      if (ok) n_out = min((uint32_t)L.len, a.k);               // core.rs:879
+    }
+    if (!ok && !a.retry_pass) {                                // visited table too small: queue for the retry pass
+      if (lane == 0) a.retry_list[atomicAdd(a.retry_count, 1u)] = qi;
+      continue;
+    }
+    // results nearest-first (core.rs:878-891); unused slots are padded
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) {
+      uint32_t e = r * 32 + lane;
+      if (e < a.k) {
+        bool have = ok && e < n_out;
+        a.ids[(size_t)qi * a.k + e] = have ? (L.id[r] & ~kExpanded) : kEmpty;
+        a.sims[(size_t)qi * a.k + e] = have ? L.sim[r] : -CUDART_INF_F;
+      }
+    }
+    for (uint32_t e = EFR * 32 + lane; e < a.k; e += 32) {     // k beyond the list capacity
+      a.ids[(size_t)qi * a.k + e] = kEmpty;
+      a.sims[(size_t)qi * a.k + e] = -CUDART_INF_F;
+    }
+    if (lane == 0) {
+      a.counts[qi] = n_out;
+      if (a.stats) {
+        a.stats[(size_t)qi * 4 + 0] = cnt.n_dist;
+        a.stats[(size_t)qi * 4 + 1] = cnt.n_adj;
+        a.stats[(size_t)qi * 4 + 2] = cnt.n_hops;
+        a.stats[(size_t)qi * 4 + 3] = (a.retry_pass ? 1u : 0u) | (ok ? 0u : 2u);
+      }
+      if (!ok) atomicOr((unsigned int*)(g.meta + kMetaError), (unsigned int)kErrVisitedOverflow);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- search_level on its own (parity tests)
+
+struct LevelArgs {
+  const float* query;
+  uint32_t entry, ef, level;
+  uint32_t* ids;    // [ef]
+  float* sims;      // [ef]
+  uint32_t* n_out;  // [1]; 0xFFFFFFFF on visited overflow
+  uint32_t vis_slots;
+  uint32_t* vis_global;
+};
+
+template <int EFR, class Dist>
+__global__ void __launch_bounds__(32) search_level_kernel(Graph g, LevelArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = lane_id();
+  Visited vis;
+  vis.tab = a.vis_global;
+  vis.mask = a.vis_slots - 1;
+  vis.shift = 32 - (31 - __clz(a.vis_slots));
+  vis.limit = a.vis_slots - a.vis_slots / 4;
+  Dist dist;
+  dist.load_query(a.query, reinterpret_cast<float*>(smem), g.dim, lane);
+  CandList<EFR> L;
+  Counters cnt = {0, 0, 0};
+  bool ok = search_layer<EFR, Dist>(g, dist, a.entry, (int)a.ef, a.level, L, vis, cnt, lane);
+  if (!ok) {
+    if (lane == 0) *a.n_out = 0xFFFFFFFFu;
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < EFR; ++r) {
+    int e = r * 32 + lane;
+    if (e < L.len) {
+      a.ids[e] = L.id[r] & ~kExpanded;
+      a.sims[e] = L.sim[r];
+    }
+  }
+  if (lane == 0) *a.n_out = (uint32_t)L.len;
+}
+
+}  // namespace hnsw

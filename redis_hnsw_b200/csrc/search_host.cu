@@ -1,0 +1,256 @@
+// Host-side dispatch of the search kernels (search.cuh) and the search entry points of the C ABI.
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/hnsw_b200.h"
+#include "index.hpp"
+
+namespace hnsw {
+
+static uint32_t next_pow2(uint64_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static bool kind_needs_smem_query(int kind) { return kind == kKindGeneric || kind == kKindScalar; }
+
+static cudaError_t dispatch_search(int kind, int efr, bool vis_smem, const LaunchCfg& c, const Graph& g, const SearchArgs& a) {
+  g_launches++;
+  switch (kind) {
+    case kKindR1: return launch_search_r1(efr, vis_smem, c, g, a);
+    case kKindR4: return launch_search_r4(efr, vis_smem, c, g, a);
+    case kKindR24: return launch_search_r24(efr, vis_smem, c, g, a);
+    case kKindGeneric: return launch_search_generic(efr, vis_smem, c, g, a);
+    default: return launch_search_scalar(efr, vis_smem, c, g, a);
+  }
+}
+
+static int dispatch_occupancy(int kind, int efr, bool vis_smem, int block, size_t smem) {
+  switch (kind) {
+    case kKindR1: return occupancy_search_r1(efr, vis_smem, block, smem);
+    case kKindR4: return occupancy_search_r4(efr, vis_smem, block, smem);
+    case kKindR24: return occupancy_search_r24(efr, vis_smem, block, smem);
+    case kKindGeneric: return occupancy_search_generic(efr, vis_smem, block, smem);
+    default: return occupancy_search_scalar(efr, vis_smem, block, smem);
+  }
+}
+
+static cudaError_t dispatch_level(int kind, int efr, const LaunchCfg& c, const Graph& g, const LevelArgs& a) {
+  g_launches++;
+  switch (kind) {
+    case kKindR1: return launch_level_r1(efr, c, g, a);
+    case kKindR4: return launch_level_r4(efr, c, g, a);
+    case kKindR24: return launch_level_r24(efr, c, g, a);
+    case kKindGeneric: return launch_level_generic(efr, c, g, a);
+    default: return launch_level_scalar(efr, c, g, a);
+  }
+}
+
+// Per-query visited-table slots for the shared-memory pass.  Starts at 32 slots per unit of ef and doubles when
+// the previous batch at this ef sent more than 1 % of its queries to the retry pass.
+uint32_t Index::pick_vis_slots(uint32_t ef) {
+  if (opt_vis_slots) return opt_vis_slots;
+  if (auto_vis_ef != ef) {
+    auto_vis_ef = ef;
+    auto_vis_slots = next_pow2(std::max<uint64_t>(1024, (uint64_t)ef * 32));
+    if (h_retry_seen) h_retry_seen[0] = h_retry_seen[1] = 0;
+  } else if (h_retry_seen && h_retry_seen[1] > 0) {
+    if ((uint64_t)h_retry_seen[0] * 100 > (uint64_t)h_retry_seen[1] && auto_vis_slots < (1u << 20)) auto_vis_slots *= 2;
+    h_retry_seen[0] = h_retry_seen[1] = 0;
+  }
+  return auto_vis_slots;
+}
+
+int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef, uint32_t* d_ids, float* d_sims,
+                         uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s) {
+  if (nq == 0) return HNSW_OK;
+  if (nq > 0x7FFFFFFFull) return fail(HNSW_ERR_INVALID, "too many queries in one batch");
+  if (!d_q || !d_ids || !d_sims || !d_counts) return fail(HNSW_ERR_INVALID, "null buffer");
+  if (k == 0) return fail(HNSW_ERR_INVALID, "k must be > 0");
+  if (ef == 0) ef = ef_construction;  // core.rs:485
+  const int efr = efr_for(ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  if (!h_retry_seen) {
+    cudaError_t e = cudaHostAlloc((void**)&h_retry_seen, 16, cudaHostAllocDefault);
+    if (e != cudaSuccess) return cuda_fail(e, "pinned alloc");
+    h_retry_seen[0] = h_retry_seen[1] = 0;
+  }
+
+  const uint32_t slots = pick_vis_slots(ef);
+  const size_t qs = kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0;
+  int block = opt_block ? opt_block : 256;
+  while (block > 32 && (size_t)(block / 32) * ((size_t)slots * 4 + qs) > max_smem) block /= 2;
+  bool vis_smem = (size_t)(block / 32) * ((size_t)slots * 4 + qs) <= max_smem;
+  if (!vis_smem) block = opt_block ? opt_block : 256;
+  int warps = block / 32;
+  if ((size_t)warps * qs > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the query staging buffer");
+  size_t smem = vis_smem ? (size_t)warps * ((size_t)slots * 4 + qs) : (size_t)warps * qs;
+  int occ = dispatch_occupancy(kind, efr, vis_smem, block, smem);
+  if (occ < 1) return fail(HNSW_ERR_CUDA, "search kernel cannot be resident (block %d, smem %zu)", block, smem);
+  if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
+  int grid = (int)std::min<uint64_t>((uint64_t)num_sms * occ, (nq + warps - 1) / warps);
+
+  // retry pass: global-memory tables, 4x the slots (at least 16K), one CTA of 4 warps per SM
+  const uint32_t big_slots = next_pow2(std::max<uint64_t>(16384, (uint64_t)slots * 4));
+  const int block2 = 128, warps2 = 4;
+  const int grid2 = (int)std::min<uint64_t>((uint64_t)num_sms, (nq + warps2 - 1) / warps2);
+  size_t vis1_bytes = vis_smem ? 0 : (size_t)grid * warps * slots * 4;
+  size_t vis2_bytes = (size_t)grid2 * warps2 * big_slots * 4;
+  int rc = ensure_scratch(s_vis, vis1_bytes + vis2_bytes);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(s_ctl, 64 + (size_t)nq * 4))) return rc;
+  uint32_t* ctl = (uint32_t*)s_ctl.p;
+  cudaError_t e = cudaMemsetAsync(ctl, 0, 64, s);
+  if (e != cudaSuccess) return cuda_fail(e, "search ctl memset");
+
+  SearchArgs a{};
+  a.queries = d_q;
+  a.nq = (uint32_t)nq;
+  a.k = k;
+  a.ef = ef;
+  a.ids = d_ids;
+  a.sims = d_sims;
+  a.counts = d_counts;
+  a.stats = d_stats;
+  a.work_counter = ctl + 0;
+  a.retry_list = ctl + 16;
+  a.retry_count = ctl + 2;
+  a.vis_slots = slots;
+  a.vis_global = (uint32_t*)s_vis.p;
+  a.retry_pass = 0;
+  LaunchCfg c{grid, block, smem, s};
+  e = dispatch_search(kind, efr, vis_smem, c, g, a);
+  if (e != cudaSuccess) return cuda_fail(e, "search_knn launch");
+
+  a.work_counter = ctl + 1;
+  a.vis_slots = big_slots;
+  a.vis_global = (uint32_t*)((char*)s_vis.p + vis1_bytes);
+  a.retry_pass = 1;
+  LaunchCfg c2{grid2, block2, (size_t)warps2 * qs, s};
+  e = dispatch_search(kind, efr, false, c2, g, a);
+  if (e != cudaSuccess) return cuda_fail(e, "search_knn retry launch");
+
+  // feedback for the adaptive table size (read at the next call; harmless if it has not landed yet)
+  e = cudaMemcpyAsync(h_retry_seen, ctl + 2, 4, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_fail(e, "retry feedback");
+  h_retry_seen[1] = (uint32_t)nq;
+  return HNSW_OK;
+}
+
+int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uint32_t* ids, float* sims,
+                       uint32_t* counts, uint32_t* stats) {
+  if (nq == 0) return HNSW_OK;
+  if (!q || !ids || !sims || !counts) return fail(HNSW_ERR_INVALID, "null buffer");
+  if (k == 0) return fail(HNSW_ERR_INVALID, "k must be > 0");
+  size_t qb = (size_t)nq * dim * 4, ib = (size_t)nq * k * 4, cb = (size_t)nq * 4, sb = stats ? (size_t)nq * 16 : 0;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  int rc = ensure_scratch(s_in, qb);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(s_out, al(ib) * 2 + al(cb) + al(sb)))) return rc;
+  char* o = (char*)s_out.p;
+  uint32_t* d_ids = (uint32_t*)o;
+  float* d_sims = (float*)(o + al(ib));
+  uint32_t* d_counts = (uint32_t*)(o + 2 * al(ib));
+  uint32_t* d_stats = stats ? (uint32_t*)(o + 2 * al(ib) + al(cb)) : nullptr;
+  cudaError_t e = cudaMemcpyAsync(s_in.p, q, qb, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "query H2D");
+  if ((rc = search_device(nq, (const float*)s_in.p, k, ef, d_ids, d_sims, d_counts, d_stats, stream))) return rc;
+  e = cudaMemcpyAsync(ids, d_ids, ib, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sims, d_sims, ib, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, cb, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats, d_stats, sb, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "search_batch");
+  if ((rc = pull_meta())) return rc;
+  if (device_error & kErrVisitedOverflow) {
+    push_meta();
+    return fail(HNSW_ERR_INVALID, "visited table overflow even in the retry pass; raise the visited_slots option");
+  }
+  return HNSW_OK;
+}
+
+int Index::search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
+                             uint32_t* n_out) {
+  const int efr = efr_for(ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  if (ep >= n_ids || h_level[ep] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", ep);
+  const uint32_t slots = next_pow2(std::max<uint64_t>(65536, (uint64_t)ef * 512));
+  int rc = ensure_scratch(s_vis, (size_t)slots * 4);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(s_in, (size_t)dim * 4))) return rc;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  if ((rc = ensure_scratch(s_out, al((size_t)ef * 4) * 2 + 256))) return rc;
+  char* o = (char*)s_out.p;
+  LevelArgs a{};
+  a.query = (const float*)s_in.p;
+  a.entry = ep;
+  a.ef = ef;
+  a.level = level;
+  a.ids = (uint32_t*)o;
+  a.sims = (float*)(o + al((size_t)ef * 4));
+  a.n_out = (uint32_t*)(o + 2 * al((size_t)ef * 4));
+  a.vis_slots = slots;
+  a.vis_global = (uint32_t*)s_vis.p;
+  cudaError_t e = cudaMemcpyAsync(s_in.p, q, (size_t)dim * 4, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "query H2D");
+  LaunchCfg c{1, 32, kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0, stream};
+  e = dispatch_level(kind, efr, c, g, a);
+  if (e != cudaSuccess) return cuda_fail(e, "search_level launch");
+  uint32_t n = 0;
+  e = cudaMemcpyAsync(&n, a.n_out, 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "search_level");
+  if (n == 0xFFFFFFFFu) return fail(HNSW_ERR_INVALID, "visited table overflow in search_level");
+  e = cudaMemcpyAsync(ids, a.ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sims, a.sims, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "search_level D2H");
+  *n_out = n;
+  return HNSW_OK;
+}
+
+}  // namespace hnsw
+
+using namespace hnsw;
+
+extern "C" {
+
+int hnsw_index_search_batch_device(hnsw_index_t* idx, uint64_t nq, const float* d_queries, uint32_t k, uint32_t ef,
+                                   uint32_t* d_ids, float* d_sims, uint32_t* d_counts, hnsw_query_stats_t* d_stats,
+                                   void* stream) {
+  IDX_OR_FAIL(idx)
+  return ix.search_device(nq, d_queries, k, ef, d_ids, d_sims, d_counts, (uint32_t*)d_stats,
+                          stream ? (cudaStream_t)stream : ix.stream);
+}
+
+int hnsw_index_search_batch(hnsw_index_t* idx, uint64_t nq, const float* queries, uint32_t k, uint32_t ef, uint32_t* ids,
+                            float* sims, uint32_t* counts, hnsw_query_stats_t* stats) {
+  IDX_OR_FAIL(idx)
+  return ix.search_host(nq, queries, k, ef, ids, sims, counts, (uint32_t*)stats);
+}
+
+int hnsw_index_search(hnsw_index_t* idx, const float* query, uint64_t n, uint32_t k, uint32_t ef, uint32_t* ids,
+                      float* sims, uint32_t* n_out) {
+  IDX_OR_FAIL(idx)
+  if (n != ix.dim) return fail(HNSW_ERR_DIM_MISMATCH, "data dimension: %llu does not match Index", (unsigned long long)n);  // core.rs:479
+  if (!n_out) return fail(HNSW_ERR_INVALID, "null n_out");
+  if (ix.entry < 0 || ix.node_count == 0) {  // core.rs:481-483
+    *n_out = 0;
+    return HNSW_OK;
+  }
+  uint32_t cnt = 0;
+  int rc = ix.search_host(1, query, k, ef, ids, sims, &cnt, nullptr);
+  if (rc) return rc;
+  *n_out = cnt;
+  return HNSW_OK;
+}
+
+int hnsw_index_search_level(hnsw_index_t* idx, const float* query, uint32_t entry, uint32_t ef, uint32_t level,
+                            uint32_t* ids, float* sims, uint32_t* n_out) {
+  IDX_OR_FAIL(idx)
+  if (!query || !ids || !sims || !n_out) return fail(HNSW_ERR_INVALID, "null buffer");
+  return ix.search_level_host(query, entry, ef, level, ids, sims, n_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every declared symbol, and the host
+layer behaves without a GPU (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import redis_hnsw_b200 as r
+
+    r.build()
+    return r
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "hnsw_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(hnsw_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = C.CDLL(built.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libhnsw_b200.so does not export %s" % name
+    from redis_hnsw_b200 import _lib
+
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device index creation must fail loudly (never silently compute on the CPU)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(built.HNSWError, match="no CUDA device"):
+        built.DeviceIndex(128, 16, 200)
+    with pytest.raises(built.HNSWError):
+        built.l2_batch(np.zeros((1, 32), np.float32), np.zeros((1, 32), np.float32))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under redis_hnsw_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "redis_hnsw_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                src = open(os.path.join(d, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+                assert "hnsw_oracle" not in src, f
+
+
+def test_row_permutation_is_a_bijection():
+    """The slab layout of distance.cuh (element i -> word ((c/V)*32 + t)*V + c%V) restated in numpy."""
+    for dim in (32, 64, 96, 128, 256, 768, 1024):
+        Cn = dim // 32
+        V = 4 if Cn % 4 == 0 else (2 if Cn % 2 == 0 else 1)
+        i = np.arange(dim)
+        c, t = i >> 5, i & 31
+        pos = ((c // V) * 32 + t) * V + (c % V)
+        assert sorted(pos.tolist()) == list(range(dim))
+        # lane t's V-wide vector g holds chunks g*V .. g*V+V-1 of residue t
+        for g in range(Cn // V):
+            for lane in (0, 7, 31):
+                words = [(g * 32 + lane) * V + r for r in range(V)]
+                elems = [int(i[pos == w][0]) for w in words]
+                assert elems == [32 * (g * V + r) + lane for r in range(V)]
+
+
+def test_level_draw_matches_reference_formula(oracle_mod):
+    import math
+
+    from redis_hnsw_b200 import data
+
+    lv = data.draw_levels(10000, 16, seed=42)
+    assert np.array_equal(lv, oracle_mod.draw_levels(10000, 16, 42))
+    rng = np.random.default_rng(42)
+    u = rng.random(10000)
+    for k in (0, 1, 17, 9999):
+        assert lv[k] == int(-math.log(u[k]) * (1.0 / math.log(16)))  # core.rs:601-605
+        assert lv[k] == oracle_mod.level_from_u(u[k], 16)
+    assert 0.05 < (lv >= 1).mean() < 0.075  # P(level >= 1) = 1/m
+
+
+def test_datasets_are_seeded():
+    from redis_hnsw_b200 import data
+
+    a, qa = data.lowrank(1000, 128, seed=5, n_queries=10)
+    b, qb = data.lowrank(1000, 128, seed=5, n_queries=10)
+    assert np.array_equal(a, b) and np.array_equal(qa, qb) and a.dtype == np.float32
+    gt = data.brute_force_topk(a, qa, 10)
+    d = ((a[None, :, :] - qa[:, None, :]) ** 2).sum(-1)
+    assert np.array_equal(np.sort(gt, 1), np.sort(np.argsort(d, 1)[:, :10], 1))
+    assert data.recall_at_k(gt, gt) == 1.0
