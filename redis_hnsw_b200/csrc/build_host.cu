@@ -1,6 +1,361 @@
 // Mutation entry points of the C ABI (insert / delete / replication).  Kernels: build.cuh.
+#define HNSW_PLAIN_BUILD_KERNELS
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
 #include "../../include/hnsw_b200.h"
 #include "index.hpp"
+
+namespace hnsw {
+
+// K2 / K4 of the batched builder do no distance arithmetic: one instantiation serves every index.
+static cudaError_t launch_plain(void (*k)(Graph, FastArgs), const LaunchCfg& c, const Graph& g, const FastArgs& a) {
+  cudaError_t e = set_smem(k, c.smem);
+  if (e != cudaSuccess) return e;
+  g_launches++;
+  k<<<c.grid, c.block, c.smem, c.stream>>>(g, a);
+  return cudaGetLastError();
+}
+
+// level = floor(-ln(u) * level_mult), u ~ U[0,1)  (core.rs:601-605); the reference saturates at usize::MAX for
+// u = 0, here the level is clamped to kMaxLevel
+static constexpr int kMaxLevel = 30;
+int Index::draw_level() {
+  rng_state += 0x9E3779B97F4A7C15ull;  // splitmix64
+  uint64_t z = rng_state;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  double x = -std::log(u) * level_mult;
+  if (!(x < (double)kMaxLevel)) return kMaxLevel;
+  return x < 0 ? 0 : (int)x;
+}
+
+int Index::set_entry(int32_t entry_, int32_t max_layer_) {
+  entry = entry_;
+  max_layer = max_layer_;
+  int32_t v[2] = {entry_, max_layer_};
+  static_assert(kMetaEntry == 0 && kMetaMaxLayer == 1, "meta layout");
+  cudaError_t e = cudaMemcpyAsync(g.meta, v, sizeof(v), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "set_entry");
+  return HNSW_OK;
+}
+
+static uint32_t list_capacity(uint32_t W) { return std::max<uint32_t>(256, 2 * W); }
+
+// list registers: the candidate list must hold ef_construction entries (search) and m_max_0 entries (re-selection)
+static int build_efr(const Index& ix) { return std::max(efr_for(ix.ef_construction), efr_for(ix.m_max_0)); }
+
+// ---------------------------------------------------------------- EXACT
+
+int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
+  if (count == 0) return HNSW_OK;
+  const int efr = build_efr(*this);
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
+  if (!exact_vis_slots) exact_vis_slots = next_pow2(std::max<uint64_t>(1u << 16, (uint64_t)ef_construction * 256));
+  const uint32_t lcap = list_capacity(g.W);
+  const uint32_t touched_cap = want_touched ? 1u << 16 : 0;
+  int rc = ensure_scratch(s_bvis, (size_t)exact_vis_slots * 4);
+  if (rc) return rc;
+  if ((rc = ensure_scratch(s_ctl, 64 + (size_t)kCtlWords * 4 + (size_t)touched_cap * 4))) return rc;
+  uint32_t* ctl = (uint32_t*)s_ctl.p;
+  cudaError_t e = cudaMemsetAsync(ctl, 0, (size_t)kCtlWords * 4, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "exact ctl memset");
+  ExactArgs a{};
+  a.first = first;
+  a.count = count;
+  a.m = m;
+  a.cap0 = m_max_0;
+  a.capU = m_max;
+  a.efc = ef_construction;
+  a.lcap = lcap;
+  a.vis_slots = exact_vis_slots;
+  a.vis = (uint32_t*)s_bvis.p;
+  a.ctl = ctl;
+  a.touched = want_touched ? ctl + kCtlWords : nullptr;
+  a.touched_cap = touched_cap;
+  size_t smem = ((size_t)((m + 31) & ~31u) + 4 * (size_t)lcap + g.W) * 4 + (kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0);
+  LaunchCfg c{1, 32, smem, stream};
+  e = run(kind, kKernExact, efr, c, g, &a);
+  if (e != cudaSuccess) return cuda_fail(e, "insert_exact launch");
+  uint32_t h[kCtlWords];
+  e = cudaMemcpyAsync(h, ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "insert_exact");
+  if ((rc = pull_meta())) return rc;
+  build_stats[0] += h[kCtlProgress];
+  build_stats[2] += h[kCtlReprunes];
+  build_stats[3] += h[kCtlDistEvals];
+  if (want_touched) {
+    uint32_t n = std::min(h[kCtlTouched], touched_cap);
+    touched.resize(n);
+    if (n) {
+      e = cudaMemcpyAsync(touched.data(), a.touched, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) return cuda_fail(e, "touched D2H");
+    }
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+  }
+  if (device_error || h[kCtlProgress] != count) {
+    int err = device_error;
+    device_error = 0;
+    push_meta();
+    return fail(HNSW_ERR_INVALID, "exact insert stopped after %u of %u nodes (device error flags 0x%x: %s)", h[kCtlProgress],
+                count, err,
+                (err & kErrVisitedOverflow) ? "visited table overflow" : (err & kErrPoolExhausted) ? "overflow-row pool exhausted"
+                                                                                                    : "adjacency list too long");
+  }
+  return HNSW_OK;
+}
+
+// ---------------------------------------------------------------- FAST
+
+struct FastPlan {
+  uint32_t slots = 0, block = 0, grid = 0;
+  bool vis_smem = false;
+  size_t smem = 0;
+};
+
+int Index::fast_batch(uint32_t first, uint32_t count) {
+  const int efr = build_efr(*this);
+  const uint32_t W = g.W, lcap = list_capacity(W);
+  // link tasks: (node, level) for level = 0 .. min(level(node), max_layer)
+  std::vector<uint32_t> task_base(count), task_node, task_level;
+  for (uint32_t b = 0; b < count; ++b) {
+    task_base[b] = (uint32_t)task_node.size();
+    int top = std::min(h_level[first + b], max_layer);
+    for (int lc = 0; lc <= top; ++lc) task_node.push_back(first + b), task_level.push_back((uint32_t)lc);
+  }
+  const uint32_t n_tasks = (uint32_t)task_node.size();
+  const uint32_t wl_cap = std::min<uint64_t>((uint64_t)n_tasks * m, 6ull * count + 1024);
+
+  // visited tables of K1 (same policy as the search path: shared memory when it fits)
+  const uint32_t slots = next_pow2(std::max<uint64_t>(1024, (uint64_t)ef_construction * 32));
+  const size_t qs = kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0;
+  int block = 256;
+  while (block > 32 && (size_t)(block / 32) * ((size_t)slots * 4 + qs) > max_smem) block /= 2;
+  const bool vis_smem = (size_t)(block / 32) * ((size_t)slots * 4 + qs) <= max_smem;
+  if (!vis_smem) block = 128;
+  const int warps = block / 32;
+  const size_t smem1 = vis_smem ? (size_t)warps * ((size_t)slots * 4 + qs) : (size_t)warps * qs;
+  const int id1 = vis_smem ? kKernBuildSearchSmem : kKernBuildSearchGlobal;
+  int occ = occupancy(kind, id1, efr, block, smem1);
+  if (occ < 1) return fail(HNSW_ERR_CUDA, "build search kernel cannot be resident (block %d, smem %zu)", block, smem1);
+  const int grid1 = (int)std::min<uint64_t>((uint64_t)num_sms * occ, (count + warps - 1) / warps);
+  const uint32_t big_slots = next_pow2(std::max<uint64_t>(1u << 16, (uint64_t)slots * 8));
+  const int block1b = 128, warps1b = 4;
+  const int grid1b = (int)std::min<uint64_t>((uint64_t)num_sms, (count + warps1b - 1) / warps1b);
+  const size_t vis1 = vis_smem ? 0 : (size_t)grid1 * warps * slots * 4;
+  const size_t vis1b = (size_t)grid1b * warps1b * big_slots * 4;
+  int rc = ensure_scratch(s_bvis, vis1 + vis1b);
+  if (rc) return rc;
+
+  // scratch layout
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += al(bytes);
+    return o;
+  };
+  const size_t o_ctl = take((size_t)kCtlWords * 4), o_tb = take((size_t)count * 4), o_tn = take((size_t)n_tasks * 4),
+               o_tl = take((size_t)n_tasks * 4), o_sel = take((size_t)n_tasks * m * 4), o_cnt = take((size_t)n_tasks * 4),
+               o_retry = take((size_t)count * 4), o_wn = take((size_t)wl_cap * 4), o_wlv = take((size_t)wl_cap * 4),
+               o_wlen = take((size_t)wl_cap * 8), o_wold = take((size_t)wl_cap * lcap * 4),
+               o_wnew = take((size_t)wl_cap * W * 4);
+  if ((rc = ensure_scratch(s_build, off))) return rc;
+  char* base = (char*)s_build.p;
+  cudaError_t e = cudaMemsetAsync(base + o_ctl, 0, (size_t)kCtlWords * 4, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_tb, task_base.data(), (size_t)count * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_tn, task_node.data(), (size_t)n_tasks * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_tl, task_level.data(), (size_t)n_tasks * 4, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "build batch upload");
+
+  FastArgs a{};
+  a.first = first;
+  a.n_new = count;
+  a.n_tasks = n_tasks;
+  a.task_base = (const uint32_t*)(base + o_tb);
+  a.task_node = (const uint32_t*)(base + o_tn);
+  a.task_level = (const uint32_t*)(base + o_tl);
+  a.sel_ids = (uint32_t*)(base + o_sel);
+  a.sel_cnt = (uint32_t*)(base + o_cnt);
+  a.m = m;
+  a.cap0 = m_max_0;
+  a.capU = m_max;
+  a.efc = ef_construction;
+  a.lcap = lcap;
+  a.ctl = (uint32_t*)(base + o_ctl);
+  a.vis_slots = slots;
+  a.vis_global = (uint32_t*)s_bvis.p;
+  a.retry_list = (uint32_t*)(base + o_retry);
+  a.retry_pass = 0;
+  a.epoch = ++epoch;
+  a.stamp0 = d_stamp0;
+  a.stampU = d_stampU;
+  a.wl_cap = wl_cap;
+  a.wl_node = (uint32_t*)(base + o_wn);
+  a.wl_level = (uint32_t*)(base + o_wlv);
+  a.wl_len = (uint32_t*)(base + o_wlen);
+  a.wl_old = (uint32_t*)(base + o_wold);
+  a.wl_new = (uint32_t*)(base + o_wnew);
+
+  // K1 (+ retry pass with large global-memory visited tables)
+  LaunchCfg c1{grid1, block, smem1, stream};
+  e = run(kind, id1, efr, c1, g, &a);
+  if (e != cudaSuccess) return cuda_fail(e, "build_search launch");
+  FastArgs a1b = a;
+  a1b.retry_pass = 1;
+  a1b.vis_slots = big_slots;
+  a1b.vis_global = (uint32_t*)((char*)s_bvis.p + vis1);
+  LaunchCfg c1b{grid1b, block1b, (size_t)warps1b * qs, stream};
+  e = run(kind, kKernBuildSearchGlobal, efr, c1b, g, &a1b);
+  if (e != cudaSuccess) return cuda_fail(e, "build_search retry launch");
+  // K2
+  {
+    const int blk = 256, w = blk / 32;
+    LaunchCfg c{(int)std::min<uint64_t>((uint64_t)num_sms * 4, (n_tasks + w - 1) / w), blk, (size_t)w * lcap * 4, stream};
+    e = launch_plain(build_link_kernel, c, g, a);
+    if (e != cudaSuccess) return cuda_fail(e, "build_link launch");
+  }
+  // K3
+  {
+    const uint32_t cap = m_max_0;
+    const uint32_t rslots = next_pow2(std::max<uint64_t>(1024, (uint64_t)cap * 64));
+    FastArgs a3 = a;
+    a3.vis_slots = rslots;
+    int blk = 256;
+    while (blk > 32 && (size_t)(blk / 32) * ((size_t)(rslots + lcap) * 4 + qs) > max_smem) blk /= 2;
+    const int w = blk / 32;
+    const size_t smem3 = (size_t)w * ((size_t)(rslots + lcap) * 4 + qs);
+    if (smem3 > max_smem) return fail(HNSW_ERR_INVALID, "m too large for the re-selection kernel");
+    int occ3 = occupancy(kind, kKernBuildReprune, efr, blk, smem3);
+    if (occ3 < 1) return fail(HNSW_ERR_CUDA, "re-selection kernel cannot be resident");
+    LaunchCfg c{(int)std::min<uint64_t>((uint64_t)num_sms * occ3, (wl_cap + w - 1) / w), blk, smem3, stream};
+    e = run(kind, kKernBuildReprune, efr, c, g, &a3);
+    if (e != cudaSuccess) return cuda_fail(e, "build_reprune launch");
+  }
+  // K4
+  {
+    const int blk = 128, w = blk / 32;
+    const size_t smem4 = (size_t)w * (2 * (size_t)lcap + W) * 4;
+    LaunchCfg c{(int)std::min<uint64_t>((uint64_t)num_sms * 4, (wl_cap + w - 1) / w), blk, smem4, stream};
+    e = launch_plain(build_apply_kernel, c, g, a);
+    if (e != cudaSuccess) return cuda_fail(e, "build_apply launch");
+  }
+  uint32_t h[kCtlWords];
+  e = cudaMemcpyAsync(h, a.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "build batch");
+  if ((rc = pull_meta())) return rc;
+  build_stats[0] += count;
+  build_stats[1] += h[kCtlWlDropped] + h[kCtlSkipped];
+  build_stats[2] += h[kCtlReprunes];
+  build_stats[3] += h[kCtlDistEvals];
+  if (device_error) {
+    int err = device_error;
+    device_error = 0;
+    push_meta();
+    if (err & (kErrPoolExhausted | kErrVisitedOverflow))
+      return fail(HNSW_ERR_INVALID, "batched insert failed (device error flags 0x%x)", err);
+    // kErrListTooLong: a hub row outgrew the edit buffer; the append was skipped (edge missing one way) -- report
+    return fail(HNSW_ERR_INVALID, "adjacency list longer than %u ids during batched insert", lcap);
+  }
+  return HNSW_OK;
+}
+
+int Index::add_fast(uint32_t first, uint32_t count) {
+  const uint32_t bmax = opt_build_batch ? opt_build_batch : 4096;
+  uint32_t pos = 0;
+  int rc;
+  while (pos < count) {
+    // batch size ramps with the graph: nodes of one batch do not see each other
+    uint32_t B = (uint32_t)std::min<uint64_t>(bmax, std::max<uint64_t>(1, node_count / 32));
+    B = std::min(B, count - pos);
+    // a node that raises max_layer becomes the enterpoint (core.rs:587-593): it goes alone
+    uint32_t cut = B;
+    for (uint32_t i = 0; i < B; ++i)
+      if (h_level[first + pos + i] > max_layer) {
+        cut = i;
+        break;
+      }
+    const bool solo_top = cut == 0;
+    if (solo_top) B = 1;
+    else B = cut;
+    // overflow rows this batch can allocate at most: one per append
+    uint64_t appends = (uint64_t)B * (m_max_0 + 8) * 4;
+    if ((rc = ensure_pool((uint64_t)pool_used + appends))) return rc;
+    if ((rc = fast_batch(first + pos, B))) return rc;
+    node_count += B;
+    if (solo_top && (rc = set_entry((int32_t)(first + pos), h_level[first + pos]))) return rc;
+    pos += B;
+  }
+  return HNSW_OK;
+}
+
+// ---------------------------------------------------------------- add_node (core.rs:383-412)
+
+int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id,
+                     bool want_touched) {
+  if (count == 0) return HNSW_OK;
+  if (!data) return fail(HNSW_ERR_INVALID, "null data");
+  if (mode != HNSW_BUILD_EXACT && mode != HNSW_BUILD_FAST) return fail(HNSW_ERR_INVALID, "unknown build mode %d", mode);
+  if (n_ids + count >= 0x7FFFFFFFull) return fail(HNSW_ERR_INVALID, "too many nodes");
+  if (!build_efr(*this)) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
+  int rc = pull_meta();  // the device owns pool_used
+  if (rc) return rc;
+  const uint32_t first = (uint32_t)n_ids;
+  // levels (core.rs:495, 601-605); the first node of an empty index draws nothing and sits on level 0 (core.rs:393-405)
+  std::vector<int32_t> lv(count);
+  uint64_t new_upper = 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    int32_t l = (levels && levels[i] >= 0) ? std::min<int32_t>(levels[i], kMaxLevel) : (int32_t)draw_level();
+    if (node_count == 0 && i == 0) l = 0;
+    lv[i] = l;
+    new_upper += (uint64_t)l;
+  }
+  if ((rc = ensure_nodes(n_ids + count))) return rc;
+  if ((rc = ensure_upper(upper_used + new_upper))) return rc;
+  std::vector<uint32_t> ub(count, kEmpty);
+  uint64_t u = upper_used;
+  for (uint64_t i = 0; i < count; ++i)
+    if (lv[i] > 0) {
+      ub[i] = (uint32_t)u;
+      u += (uint64_t)lv[i];
+    }
+  if ((rc = upload_vectors(data, first, count))) return rc;
+  cudaError_t e = cudaMemcpyAsync(g.level + first, lv.data(), count * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(g.upper_base + first, ub.data(), count * 4, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "level upload");
+  h_level.insert(h_level.end(), lv.begin(), lv.end());
+  h_upper_base.insert(h_upper_base.end(), ub.begin(), ub.end());
+  n_ids += count;
+  upper_used = u;
+  touched.clear();
+  if (first_id) *first_id = first;
+
+  uint32_t start = 0;
+  if (node_count == 0) {  // core.rs:393-405
+    if ((rc = set_entry((int32_t)first, 0))) return rc;
+    node_count = 1;
+    start = 1;
+  }
+  const uint32_t rest = (uint32_t)count - start;
+  if (mode == HNSW_BUILD_EXACT) {
+    if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)rest * (m_max_0 + 8) * 2 + 4096))) return rc;
+    rc = add_exact(first + start, rest, want_touched);
+    if (!rc) node_count += rest;
+    return rc;
+  }
+  return add_fast(first + start, rest);
+}
+
+}  // namespace hnsw
 
 using namespace hnsw;
 
@@ -8,15 +363,14 @@ extern "C" {
 
 int hnsw_index_add(hnsw_index_t* idx, const float* data, uint64_t n, int32_t level, uint32_t* out_id) {
   IDX_OR_FAIL(idx)
-  (void)data, (void)n, (void)level, (void)out_id;
-  return fail(HNSW_ERR_INVALID, "hnsw_index_add: not implemented yet");
+  if (n != ix.dim) return fail(HNSW_ERR_DIM_MISMATCH, "data dimension: %llu does not match Index", (unsigned long long)n);  // core.rs:390
+  return ix.add_batch(1, data, &level, HNSW_BUILD_EXACT, out_id, true);
 }
 
 int hnsw_index_add_batch(hnsw_index_t* idx, uint64_t count, const float* data, const int32_t* levels, int mode,
                          uint32_t* first_id) {
   IDX_OR_FAIL(idx)
-  (void)count, (void)data, (void)levels, (void)mode, (void)first_id;
-  return fail(HNSW_ERR_INVALID, "hnsw_index_add_batch: not implemented yet");
+  return ix.add_batch(count, data, levels, mode, first_id, false);
 }
 
 int hnsw_index_touched(hnsw_index_t* idx, uint32_t* ids, uint64_t cap, uint64_t* n) {
@@ -73,14 +427,15 @@ int hnsw_index_prepare_replica(hnsw_index_t* idx, const uint64_t* layout8) {
   int rc;
   if (ix.cap_nodes < layout8[0]) {
     ix.cap_nodes = 0;  // forget the small initial allocation: grow_buf copies min(old,new)=0 bytes
-    void* olds[] = {ix.g.vecs, ix.g.adj0, ix.g.ovf0, ix.g.upper_base, ix.g.level};
+    void* olds[] = {ix.g.vecs, ix.g.adj0, ix.g.ovf0, ix.g.upper_base, ix.g.level, ix.d_stamp0};
     for (void* p : olds) cudaFree(p);
     ix.g.vecs = nullptr, ix.g.adj0 = nullptr, ix.g.ovf0 = nullptr, ix.g.upper_base = nullptr, ix.g.level = nullptr;
+    ix.d_stamp0 = nullptr;
     if ((rc = ix.ensure_nodes(layout8[0]))) return rc;
   }
   if (ix.cap_upper < layout8[1]) {
-    cudaFree(ix.g.adjU), cudaFree(ix.g.ovfU);
-    ix.g.adjU = nullptr, ix.g.ovfU = nullptr, ix.cap_upper = 0;
+    cudaFree(ix.g.adjU), cudaFree(ix.g.ovfU), cudaFree(ix.d_stampU);
+    ix.g.adjU = nullptr, ix.g.ovfU = nullptr, ix.d_stampU = nullptr, ix.cap_upper = 0;
     if ((rc = ix.ensure_upper(layout8[1]))) return rc;
   }
   if (ix.g.pool_cap < layout8[2]) {

@@ -26,6 +26,7 @@ enum Meta : int {
 };
 constexpr int kErrPoolExhausted = 1;
 constexpr int kErrVisitedOverflow = 2;
+constexpr int kErrListTooLong = 4;  // an adjacency list outgrew the builder's edit buffer
 
 // Read-only (for search) / mutable (for build) view of the graph in HBM.
 //
@@ -36,6 +37,7 @@ constexpr int kErrVisitedOverflow = 2;
 //   upper_base [n]      u32   first upper row of the node (levels 1..level), or kEmpty for level-0-only nodes
 //   adjU       [nU][W]  u32   upper-level rows: row = upper_base[node] + (level - 1)
 //   ovfU       [nU]     u32
+//   locks      [2^k]    u32   hashed row locks, only used by the batched builder
 //   pool       [P][32]  u32   overflow rows: 31 ids + link.  The reference does not bound a node's degree
 //                             (core.rs:793-795 adds back-edges without a cap check), so lists can outgrow W.
 struct Graph {
@@ -48,6 +50,8 @@ struct Graph {
   uint32_t* ovfU;
   uint32_t* pool;
   int32_t* meta;
+  uint32_t* locks;  // hashed row locks of the batched builder (build.cuh)
+  int lock_shift;   // 32 - log2(number of locks)
   uint32_t W;
   uint32_t dim;
   uint32_t pool_cap;

@@ -121,6 +121,7 @@ int Index::ensure_nodes(uint64_t n) {
   GROW(g.ovf0, 4, 0xFF)
   GROW(g.upper_base, 4, 0xFF)
   GROW(g.level, 4, 0xFF)
+  GROW(d_stamp0, 4, 0)
 #undef GROW
   cap_nodes = nc;
   return HNSW_OK;
@@ -133,6 +134,8 @@ int Index::ensure_upper(uint64_t rows) {
   if (e != cudaSuccess) return cuda_fail(e, "grow adjU");
   e = grow_buf((void**)&g.ovfU, (size_t)cap_upper * 4, (size_t)nc * 4, 0xFF, stream);
   if (e != cudaSuccess) return cuda_fail(e, "grow ovfU");
+  e = grow_buf((void**)&d_stampU, (size_t)cap_upper * 4, (size_t)nc * 4, 0, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "grow stampU");
   cap_upper = nc;
   return HNSW_OK;
 }
@@ -187,8 +190,9 @@ int Index::pull_meta() {
 
 Index::~Index() {
   if (cudaSetDevice(device) != cudaSuccess) return;
-  void* ptrs[] = {g.vecs, g.adj0, g.ovf0, g.upper_base, g.level, g.adjU, g.ovfU, g.pool, g.meta,
-                  s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p};
+  void* ptrs[] = {g.vecs, g.adj0, g.ovf0, g.upper_base, g.level, g.adjU, g.ovfU, g.pool, g.meta, g.locks,
+                  d_stamp0, d_stampU, s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p, s_bvis.p};
+  if (h_retry_seen) cudaFreeHost(h_retry_seen);
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
@@ -442,6 +446,13 @@ int hnsw_index_create(uint32_t data_dim, uint32_t m, uint32_t ef_construction, i
   if (!rc) {
     e = cudaMalloc((void**)&ix.g.meta, sizeof(int32_t) * kMetaCount);
     if (e != cudaSuccess) rc = cuda_fail(e, "meta alloc");
+  }
+  if (!rc) {
+    const int lock_bits = 20;
+    e = cudaMalloc((void**)&ix.g.locks, sizeof(uint32_t) << lock_bits);
+    if (e == cudaSuccess) e = cudaMemset(ix.g.locks, 0, sizeof(uint32_t) << lock_bits);
+    if (e != cudaSuccess) rc = cuda_fail(e, "lock table alloc");
+    ix.g.lock_shift = 32 - lock_bits;
   }
   if (!rc) rc = ix.ensure_nodes(1024);
   if (!rc) rc = ix.ensure_upper(1024);

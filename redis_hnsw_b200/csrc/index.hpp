@@ -55,8 +55,14 @@ struct Index {
   uint32_t auto_vis_ef = 0, auto_vis_slots = 0;  // adaptive visited-table size for the last-used ef
   uint32_t* h_retry_seen = nullptr;              // pinned: retry count of the previous async search
 
+  // builder state (build_host.cu)
+  uint32_t* d_stamp0 = nullptr;   // [cap_nodes] worklist de-duplication stamps (level-0 rows)
+  uint32_t* d_stampU = nullptr;   // [cap_upper]
+  uint32_t epoch = 0;
+  uint32_t exact_vis_slots = 0;
+
   // scratch
-  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage;
+  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis;
 
   ~Index();
   int use_device();
@@ -81,7 +87,18 @@ struct Index {
   int search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
                         uint32_t* n_out);
   uint32_t pick_vis_slots(uint32_t ef);
+
+  // insert (build_host.cu)
+  int add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id, bool want_touched);
+  int add_exact(uint32_t first, uint32_t count, bool want_touched);
+  int add_fast(uint32_t first, uint32_t count);
+  int fast_batch(uint32_t first, uint32_t count);
+  int set_entry(int32_t entry, int32_t max_layer);
+  int draw_level();
 };
+
+uint32_t next_pow2(uint64_t v);
+bool kind_needs_smem_query(int kind);
 
 }  // namespace hnsw
 

@@ -1,5 +1,6 @@
 // Launch plumbing shared by the per-distance-mode translation units (one TU per Dist keeps nvcc parallel).
 #pragma once
+#include "build.cuh"
 #include "search.cuh"
 
 namespace hnsw {
@@ -23,99 +24,100 @@ inline int efr_for(uint32_t ef) {
   return 0;
 }
 
-template <int EFR, class Dist, bool VS>
-cudaError_t launch_search_one(const LaunchCfg& c, const Graph& g, const SearchArgs& a) {
-  auto k = search_knn_kernel<EFR, Dist, VS>;
-  if (c.smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
-    if (e != cudaSuccess) return e;
-  }
+// which kernel of a kind
+enum KernelId : int {
+  kKernSearchSmem = 0,   // search_knn_kernel, visited table in shared memory
+  kKernSearchGlobal = 1, // search_knn_kernel, visited table in global memory
+  kKernLevel = 2,        // search_level_kernel
+  kKernBuildSearchSmem = 3,
+  kKernBuildSearchGlobal = 4,
+  kKernBuildReprune = 5,
+  kKernExact = 6,
+};
+
+// kernel arguments are passed type-erased so that one entry point per kind serves every kernel
+struct KernelArgs {
+  const Graph* g;
+  const void* a;  // SearchArgs / LevelArgs / FastArgs / ExactArgs
+};
+
+template <class K>
+inline cudaError_t set_smem(K k, size_t smem) {
+  if (smem > 48 * 1024) return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaSuccess;
+}
+
+template <class K, class A>
+inline cudaError_t launch_k(K k, const LaunchCfg& c, const Graph& g, const A& a) {
+  cudaError_t e = set_smem(k, c.smem);
+  if (e != cudaSuccess) return e;
   k<<<c.grid, c.block, c.smem, c.stream>>>(g, a);
   return cudaGetLastError();
 }
 
-template <class Dist>
-cudaError_t launch_search(int efr, bool vis_smem, const LaunchCfg& c, const Graph& g, const SearchArgs& a) {
-#define HNSW_CASE(E)                                                       \
-  case E:                                                                  \
-    return vis_smem ? launch_search_one<E, Dist, true>(c, g, a) : launch_search_one<E, Dist, false>(c, g, a);
-  switch (efr) {
-    HNSW_CASE(1)
-    HNSW_CASE(2)
-    HNSW_CASE(4)
-    HNSW_CASE(8)
-    HNSW_CASE(16)
-  }
-#undef HNSW_CASE
-  return cudaErrorInvalidValue;
-}
-
-template <class Dist>
-cudaError_t launch_level(int efr, const LaunchCfg& c, const Graph& g, const LevelArgs& a) {
-#define HNSW_CASE(E)                                                      \
-  case E:                                                                 \
-    search_level_kernel<E, Dist><<<1, 32, c.smem, c.stream>>>(g, a);      \
-    return cudaGetLastError();
-  switch (efr) {
-    HNSW_CASE(1)
-    HNSW_CASE(2)
-    HNSW_CASE(4)
-    HNSW_CASE(8)
-    HNSW_CASE(16)
-  }
-#undef HNSW_CASE
-  return cudaErrorInvalidValue;
-}
-
-// resident CTAs per SM the search kernel can reach with `block` threads and `smem` dynamic bytes
-template <class Dist>
-int occupancy_search(int efr, bool vis_smem, int block, size_t smem) {
+template <class K>
+inline int occ_k(K k, int block, size_t smem) {
+  if (set_smem(k, smem) != cudaSuccess) return 0;
   int n = 0;
-#define HNSW_CASE(E)                                                                                              \
-  case E:                                                                                                         \
-    if (vis_smem) {                                                                                               \
-      if (smem > 48 * 1024)                                                                                       \
-        cudaFuncSetAttribute(search_knn_kernel<E, Dist, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                             (int)smem);                                                                          \
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_knn_kernel<E, Dist, true>, block, smem);           \
-    } else {                                                                                                      \
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, search_knn_kernel<E, Dist, false>, block, smem);          \
-    }                                                                                                             \
-    break;
-  switch (efr) {
-    HNSW_CASE(1)
-    HNSW_CASE(2)
-    HNSW_CASE(4)
-    HNSW_CASE(8)
-    HNSW_CASE(16)
-  }
-#undef HNSW_CASE
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, block, smem) != cudaSuccess) return 0;
   return n;
 }
 
-// entry points defined in kernels_<kind>.cu
-#define HNSW_DECL_KIND(NAME)                                                                                   \
-  cudaError_t launch_search_##NAME(int efr, bool vis_smem, const LaunchCfg& c, const Graph& g, const SearchArgs& a); \
-  cudaError_t launch_level_##NAME(int efr, const LaunchCfg& c, const Graph& g, const LevelArgs& a);            \
-  int occupancy_search_##NAME(int efr, bool vis_smem, int block, size_t smem);
-HNSW_DECL_KIND(r1)
-HNSW_DECL_KIND(r4)
-HNSW_DECL_KIND(r24)
-HNSW_DECL_KIND(generic)
-HNSW_DECL_KIND(scalar)
-#undef HNSW_DECL_KIND
-
-#define HNSW_DEFINE_KIND(NAME, DIST)                                                                            \
-  namespace hnsw {                                                                                              \
-  cudaError_t launch_search_##NAME(int efr, bool vis_smem, const LaunchCfg& c, const Graph& g, const SearchArgs& a) { \
-    return launch_search<DIST>(efr, vis_smem, c, g, a);                                                         \
-  }                                                                                                             \
-  cudaError_t launch_level_##NAME(int efr, const LaunchCfg& c, const Graph& g, const LevelArgs& a) {            \
-    return launch_level<DIST>(efr, c, g, a);                                                                    \
-  }                                                                                                             \
-  int occupancy_search_##NAME(int efr, bool vis_smem, int block, size_t smem) {                                 \
-    return occupancy_search<DIST>(efr, vis_smem, block, smem);                                                  \
-  }                                                                                                             \
+// launch (occupancy_only = false) or query resident CTAs per SM (occupancy_only = true, returned as a
+// non-negative int through *occ)
+template <int EFR, class Dist>
+cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ) {
+#define HNSW_RUN(KERNEL, ARGT)                                             \
+  {                                                                        \
+    auto k = KERNEL;                                                       \
+    if (occupancy_only) {                                                  \
+      *occ = occ_k(k, c.block, c.smem);                                    \
+      return cudaSuccess;                                                  \
+    }                                                                      \
+    return launch_k(k, c, *ka.g, *static_cast<const ARGT*>(ka.a));         \
   }
+  switch (id) {
+    case kKernSearchSmem: HNSW_RUN((search_knn_kernel<EFR, Dist, true>), SearchArgs)
+    case kKernSearchGlobal: HNSW_RUN((search_knn_kernel<EFR, Dist, false>), SearchArgs)
+    case kKernLevel: HNSW_RUN((search_level_kernel<EFR, Dist>), LevelArgs)
+    case kKernBuildSearchSmem: HNSW_RUN((build_search_kernel<EFR, Dist, true>), FastArgs)
+    case kKernBuildSearchGlobal: HNSW_RUN((build_search_kernel<EFR, Dist, false>), FastArgs)
+    case kKernBuildReprune: HNSW_RUN((build_reprune_kernel<EFR, Dist>), FastArgs)
+    case kKernExact: HNSW_RUN((insert_exact_kernel<EFR, Dist>), ExactArgs)
+  }
+#undef HNSW_RUN
+  return cudaErrorInvalidValue;
+}
+
+template <class Dist>
+cudaError_t run_kind(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ) {
+  switch (efr) {
+    case 1: return run_kernel<1, Dist>(id, c, ka, occupancy_only, occ);
+    case 2: return run_kernel<2, Dist>(id, c, ka, occupancy_only, occ);
+    case 4: return run_kernel<4, Dist>(id, c, ka, occupancy_only, occ);
+    case 8: return run_kernel<8, Dist>(id, c, ka, occupancy_only, occ);
+    case 16: return run_kernel<16, Dist>(id, c, ka, occupancy_only, occ);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// entry points defined in kernels_<kind>.cu
+cudaError_t run_kind_r1(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ);
+cudaError_t run_kind_r4(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ);
+cudaError_t run_kind_r24(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ);
+cudaError_t run_kind_generic(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ);
+cudaError_t run_kind_scalar(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ);
+
+#define HNSW_DEFINE_KIND(NAME, DIST)                                                                             \
+  namespace hnsw {                                                                                               \
+  cudaError_t run_kind_##NAME(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only,    \
+                              int* occ) {                                                                        \
+    return run_kind<DIST>(id, efr, c, ka, occupancy_only, occ);                                                  \
+  }                                                                                                              \
+  }
+
+// dispatch on the index's distance kind (search_host.cu)
+cudaError_t run(int kind, int id, int efr, const LaunchCfg& c, const Graph& g, const void* args);
+int occupancy(int kind, int id, int efr, int block, size_t smem);
 
 }  // namespace hnsw

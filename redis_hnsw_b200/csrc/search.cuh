@@ -158,6 +158,13 @@ struct DistReg {
 #pragma unroll
     for (int c = 0; c < C; ++c) q[c] = qn[32 * c + lane];
   }
+  // query = the stored vector of `node` (insert path: the new node / the node being re-selected)
+  __device__ __forceinline__ void load_query_slab(const Graph& g, uint32_t node, float*, int lane) {
+    RowRegs<C> r;
+    load_row_regs<C>(g.vecs + (size_t)node * (32 * C), lane, r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) q[c] = r.x[c];
+  }
   __device__ __forceinline__ float one(const Graph& g, uint32_t nid, int lane) const {
     RowRegs<C> r;
     load_row_regs<C>(g.vecs + (size_t)nid * (32 * C), lane, r);
@@ -200,7 +207,17 @@ struct DistGeneric {
   __device__ __forceinline__ void load_query(const float* __restrict__ qn, float* smem_q, uint32_t dim, int lane) {
     C = dim / 32;
     V = dist_vec_width(dim);
+    __syncwarp();
     for (uint32_t i = lane; i < dim; i += 32) smem_q[permuted_pos(i, V)] = qn[i];
+    qs = smem_q;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void load_query_slab(const Graph& g, uint32_t node, float* smem_q, int lane) {
+    C = g.dim / 32;
+    V = dist_vec_width(g.dim);
+    const float* row = g.vecs + (size_t)node * g.dim;  // slab rows are already lane-permuted
+    __syncwarp();
+    for (uint32_t i = lane; i < g.dim; i += 32) smem_q[i] = row[i];
     qs = smem_q;
     __syncwarp();
   }
@@ -239,7 +256,16 @@ struct DistScalar {
   uint32_t dim;
   __device__ __forceinline__ void load_query(const float* __restrict__ qn, float* smem_q, uint32_t d, int lane) {
     dim = d;
+    __syncwarp();
     for (uint32_t i = lane; i < d; i += 32) smem_q[i] = qn[i];
+    qs = smem_q;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void load_query_slab(const Graph& g, uint32_t node, float* smem_q, int lane) {
+    dim = g.dim;
+    const float* row = g.vecs + (size_t)node * g.dim;
+    __syncwarp();
+    for (uint32_t i = lane; i < g.dim; i += 32) smem_q[i] = row[i];
     qs = smem_q;
     __syncwarp();
   }

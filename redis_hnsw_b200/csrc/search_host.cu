@@ -7,44 +7,38 @@
 
 namespace hnsw {
 
-static uint32_t next_pow2(uint64_t v) {
+uint32_t next_pow2(uint64_t v) {
   uint32_t p = 1;
   while (p < v) p <<= 1;
   return p;
 }
 
-static bool kind_needs_smem_query(int kind) { return kind == kKindGeneric || kind == kKindScalar; }
+bool kind_needs_smem_query(int kind) { return kind == kKindGeneric || kind == kKindScalar; }
 
-static cudaError_t dispatch_search(int kind, int efr, bool vis_smem, const LaunchCfg& c, const Graph& g, const SearchArgs& a) {
+cudaError_t run(int kind, int id, int efr, const LaunchCfg& c, const Graph& g, const void* args) {
   g_launches++;
+  KernelArgs ka{&g, args};
   switch (kind) {
-    case kKindR1: return launch_search_r1(efr, vis_smem, c, g, a);
-    case kKindR4: return launch_search_r4(efr, vis_smem, c, g, a);
-    case kKindR24: return launch_search_r24(efr, vis_smem, c, g, a);
-    case kKindGeneric: return launch_search_generic(efr, vis_smem, c, g, a);
-    default: return launch_search_scalar(efr, vis_smem, c, g, a);
+    case kKindR1: return run_kind_r1(id, efr, c, ka, false, nullptr);
+    case kKindR4: return run_kind_r4(id, efr, c, ka, false, nullptr);
+    case kKindR24: return run_kind_r24(id, efr, c, ka, false, nullptr);
+    case kKindGeneric: return run_kind_generic(id, efr, c, ka, false, nullptr);
+    default: return run_kind_scalar(id, efr, c, ka, false, nullptr);
   }
 }
 
-static int dispatch_occupancy(int kind, int efr, bool vis_smem, int block, size_t smem) {
+int occupancy(int kind, int id, int efr, int block, size_t smem) {
+  LaunchCfg c{1, block, smem, nullptr};
+  KernelArgs ka{nullptr, nullptr};
+  int occ = 0;
   switch (kind) {
-    case kKindR1: return occupancy_search_r1(efr, vis_smem, block, smem);
-    case kKindR4: return occupancy_search_r4(efr, vis_smem, block, smem);
-    case kKindR24: return occupancy_search_r24(efr, vis_smem, block, smem);
-    case kKindGeneric: return occupancy_search_generic(efr, vis_smem, block, smem);
-    default: return occupancy_search_scalar(efr, vis_smem, block, smem);
+    case kKindR1: run_kind_r1(id, efr, c, ka, true, &occ); break;
+    case kKindR4: run_kind_r4(id, efr, c, ka, true, &occ); break;
+    case kKindR24: run_kind_r24(id, efr, c, ka, true, &occ); break;
+    case kKindGeneric: run_kind_generic(id, efr, c, ka, true, &occ); break;
+    default: run_kind_scalar(id, efr, c, ka, true, &occ); break;
   }
-}
-
-static cudaError_t dispatch_level(int kind, int efr, const LaunchCfg& c, const Graph& g, const LevelArgs& a) {
-  g_launches++;
-  switch (kind) {
-    case kKindR1: return launch_level_r1(efr, c, g, a);
-    case kKindR4: return launch_level_r4(efr, c, g, a);
-    case kKindR24: return launch_level_r24(efr, c, g, a);
-    case kKindGeneric: return launch_level_generic(efr, c, g, a);
-    default: return launch_level_scalar(efr, c, g, a);
-  }
+  return occ;
 }
 
 // Per-query visited-table slots for the shared-memory pass.  Starts at 32 slots per unit of ef and doubles when
@@ -86,7 +80,7 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   int warps = block / 32;
   if ((size_t)warps * qs > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the query staging buffer");
   size_t smem = vis_smem ? (size_t)warps * ((size_t)slots * 4 + qs) : (size_t)warps * qs;
-  int occ = dispatch_occupancy(kind, efr, vis_smem, block, smem);
+  int occ = occupancy(kind, vis_smem ? kKernSearchSmem : kKernSearchGlobal, efr, block, smem);
   if (occ < 1) return fail(HNSW_ERR_CUDA, "search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
   int grid = (int)std::min<uint64_t>((uint64_t)num_sms * occ, (nq + warps - 1) / warps);
@@ -120,7 +114,7 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   a.vis_global = (uint32_t*)s_vis.p;
   a.retry_pass = 0;
   LaunchCfg c{grid, block, smem, s};
-  e = dispatch_search(kind, efr, vis_smem, c, g, a);
+  e = run(kind, vis_smem ? kKernSearchSmem : kKernSearchGlobal, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "search_knn launch");
 
   a.work_counter = ctl + 1;
@@ -128,7 +122,7 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   a.vis_global = (uint32_t*)((char*)s_vis.p + vis1_bytes);
   a.retry_pass = 1;
   LaunchCfg c2{grid2, block2, (size_t)warps2 * qs, s};
-  e = dispatch_search(kind, efr, false, c2, g, a);
+  e = run(kind, kKernSearchGlobal, efr, c2, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "search_knn retry launch");
 
   // feedback for the adaptive table size (read at the next call; harmless if it has not landed yet)
@@ -195,7 +189,7 @@ int Index::search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t 
   cudaError_t e = cudaMemcpyAsync(s_in.p, q, (size_t)dim * 4, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return cuda_fail(e, "query H2D");
   LaunchCfg c{1, 32, kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0, stream};
-  e = dispatch_level(kind, efr, c, g, a);
+  e = run(kind, kKernLevel, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "search_level launch");
   uint32_t n = 0;
   e = cudaMemcpyAsync(&n, a.n_out, 4, cudaMemcpyDeviceToHost, stream);
