@@ -51,6 +51,9 @@ struct Index {
   // options / adaptive state
   uint32_t opt_vis_slots = 0;
   int opt_ctas_per_sm = 0, opt_block = 0;
+  int opt_search_impl = 0;        // 0 auto, 1 = register-staged kernel (search.cuh), 2 = TMA-staged kernel (search2.cuh)
+  int opt_stage_rows = 0;         // rows per TMA stage (8 / 16 / 32), 0 = auto
+  uint32_t opt_recent_slots = 0;  // direct-mapped visited slots of the TMA-staged kernel, 0 = auto
   uint32_t opt_build_batch = 0;
   uint32_t auto_vis_ef = 0, auto_vis_slots = 0;  // adaptive visited-table size for the last-used ef
   uint32_t* h_retry_seen = nullptr;              // pinned: retry count of the previous async search
@@ -87,6 +90,8 @@ struct Index {
   int search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
                         uint32_t* n_out);
   uint32_t pick_vis_slots(uint32_t ef);
+  int search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef, int efr, uint32_t* d_ids, float* d_sims,
+                     uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s);
 
   // insert (build_host.cu)
   int add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id, bool want_touched);

@@ -2,6 +2,7 @@
 #pragma once
 #include "build.cuh"
 #include "search.cuh"
+#include "search2.cuh"
 
 namespace hnsw {
 
@@ -33,6 +34,9 @@ enum KernelId : int {
   kKernBuildSearchGlobal = 4,
   kKernBuildReprune = 5,
   kKernExact = 6,
+  kKernSearch2S8 = 7,    // search_knn2_kernel (TMA-staged rows), 8 / 16 / 32 rows per stage
+  kKernSearch2S16 = 8,
+  kKernSearch2S32 = 9,
 };
 
 // kernel arguments are passed type-erased so that one entry point per kind serves every kernel
@@ -84,6 +88,13 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
     case kKernBuildSearchGlobal: HNSW_RUN((build_search_kernel<EFR, Dist, false>), FastArgs)
     case kKernBuildReprune: HNSW_RUN((build_reprune_kernel<EFR, Dist>), FastArgs)
     case kKernExact: HNSW_RUN((insert_exact_kernel<EFR, Dist>), ExactArgs)
+  }
+  if constexpr (Dist::kStaged) {
+    switch (id) {
+      case kKernSearch2S8: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8>), SearchArgs)
+      case kKernSearch2S16: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16>), SearchArgs)
+      case kKernSearch2S32: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32>), SearchArgs)
+    }
   }
 #undef HNSW_RUN
   return cudaErrorInvalidValue;

@@ -153,6 +153,7 @@ struct DistReg {
   static constexpr int C = C_;
   static constexpr int U = (C <= 4) ? 4 : ((C <= 8) ? 2 : 1);  // rows in flight per lane
   static constexpr bool kNeedsSmemQuery = false;
+  static constexpr bool kStaged = true;  // search2.cuh has a TMA-staged kernel for this dimension
   float q[C];
   __device__ __forceinline__ void load_query(const float* __restrict__ qn, float*, uint32_t, int lane) {
 #pragma unroll
@@ -201,6 +202,7 @@ struct DistReg {
 // dim % 32 == 0, any size: permuted query in shared memory.
 struct DistGeneric {
   static constexpr bool kNeedsSmemQuery = true;
+  static constexpr bool kStaged = false;
   const float* qs;
   uint32_t C;
   int V;
@@ -252,6 +254,7 @@ struct DistGeneric {
 // dim % 32 != 0: reference scalar fold, one lane per row, natural-order query in shared memory.
 struct DistScalar {
   static constexpr bool kNeedsSmemQuery = true;
+  static constexpr bool kStaged = false;
   const float* qs;
   uint32_t dim;
   __device__ __forceinline__ void load_query(const float* __restrict__ qn, float* smem_q, uint32_t d, int lane) {

@@ -1,0 +1,333 @@
+// search_knn, second generation: TMA-staged vector rows (reference: src/hnsw/core.rs:607-675, 865-892).
+//
+// Same formulation as search.cuh (one warp per query, sorted ef-list with "expanded" flags in registers), but the
+// distance batch of a hop is restructured around the memory system of a B200 SM:
+//   * the neighbour vectors of one adjacency chunk (<= 32 rows) are fetched with one bulk-async copy each
+//     (cp.async.bulk, the non-tensor TMA path; SASS UBLKCP) into a per-warp shared-memory stage and complete on a
+//     per-warp mbarrier, so a warp keeps up to S rows (S * 4 * dim bytes) in flight without holding them in
+//     registers;
+//   * every lane reads its 16-byte slices of each staged row (LDS.128, conflict-free thanks to the lane-permuted
+//     slab layout), forms the per-lane partial of metrics.rs:55-69, and the S partials are reduced TOGETHER by a
+//     transposed butterfly: the same five exchange steps (xor 8, 16, 4, 1, 2 — the reference's hsum tree,
+//     metrics.rs:25-42,71-74) but with rows paired so each step halves the number of live registers.
+//     31 shuffles for 32 rows instead of 160, and bit-identical sums (every add has the reference's operand pair);
+//   * the visited set is a direct-mapped exact-tag table: a hit proves "already evaluated", a conflict simply
+//     forgets the older id.  Forgetting is harmless: a node that was evaluated and is not in the list lost against
+//     the list's worst entry and will lose again (core.rs:657), and a node that is still in the list is caught by an
+//     explicit membership test before insertion.  Results are identical to the exact set; only the number of
+//     distance evaluations can exceed the reference's (reported by the kernel);
+//   * the adjacency row of every admitted candidate is prefetched into L2 (all members of the final list get
+//     expanded), taking one DRAM round trip out of the dependent chain of a hop.
+#pragma once
+#include <math_constants.h>
+
+#include "search.cuh"
+
+namespace hnsw {
+
+// ---------------------------------------------------------------- mbarrier / bulk copy (PTX)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// global -> shared bulk copy completing on an mbarrier (bytes: multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---------------------------------------------------------------- transposed hsum of S row partials
+
+// On entry acc[r] is this lane's partial of row r (metrics.rs:55-69).  On return lane r (< S) holds the complete
+// reference-ordered sum of row r, negated (metrics.rs:75).
+template <int S>
+__device__ __forceinline__ float reduce_rows(float (&acc)[S], int lane) {
+  constexpr int kOff[5] = {8, 16, 4, 1, 2};  // metrics.rs:71-74 (e1+e2)+(e3+e4) | :37-39 lo+hi | :25-32
+#pragma unroll
+  for (int lev = 0; lev < 5; ++lev) {
+    const int off = kOff[lev];
+    const bool up = (lane & off) != 0;
+    const int n = S >> lev;  // live registers before this step
+    if (n >= 2) {
+#pragma unroll
+      for (int i = 0; i < n / 2; ++i) {
+        float a = acc[2 * i], b = acc[2 * i + 1];
+        float send = up ? a : b, keep = up ? b : a;
+        acc[i] = __fadd_rn(keep, __shfl_xor_sync(kFull, send, off));
+      }
+    } else {
+      acc[0] = __fadd_rn(acc[0], __shfl_xor_sync(kFull, acc[0], off));
+    }
+  }
+  // lane t = (b4 b3 b2 b1 b0) now holds row 16*b1 + 8*b0 + 4*b2 + 2*b4 + b3 (missing bits for S < 32 are free);
+  // route row r to lane r
+  const int r = lane;
+  const int src = (((r >> 1) & 1) << 4) | ((r & 1) << 3) | (((r >> 2) & 1) << 2) | (((r >> 4) & 1) << 1) | ((r >> 3) & 1);
+  return -__shfl_sync(kFull, acc[0], src);
+}
+
+// ---------------------------------------------------------------- lossy exact-tag visited table
+
+struct Recent {
+  uint32_t* tab;
+  uint32_t n4;  // slots / 4
+  int shift;    // 32 - log2(slots)
+  __device__ __forceinline__ void clear(int lane) {
+    uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+    uint4* t = reinterpret_cast<uint4*>(tab);
+    for (uint32_t i = lane; i < n4; i += 32) t[i] = e;
+    __syncwarp();
+  }
+  // true if `nid` was NOT found (and is now remembered)
+  __device__ __forceinline__ bool test_and_set(uint32_t nid) {
+    uint32_t slot = (nid * 2654435761u) >> shift;
+    if (tab[slot] == nid) return false;
+    tab[slot] = nid;
+    return true;
+  }
+};
+
+template <int EFR>
+__device__ __forceinline__ bool list_has(const CandList<EFR>& L, uint32_t x) {
+  bool hit = false;
+#pragma unroll
+  for (int r = 0; r < EFR; ++r) hit |= __any_sync(kFull, L.id[r] != kEmpty && (L.id[r] & ~kExpanded) == x);
+  return hit;
+}
+
+// ---------------------------------------------------------------- per-warp context
+
+template <int C, int S>
+struct Warp2 {
+  static constexpr uint32_t kRowBytes = 128u * C;
+  float q[C];          // q[c] = query[32c + lane]
+  const float4* stage; // [S][C*8] float4 per... (S rows of 4*dim bytes)
+  uint32_t stage_s;    // shared-space address of the stage
+  uint32_t* ids;       // [32] compacted neighbour ids of the round
+  uint32_t bar;        // shared-space address of the mbarrier
+  uint32_t parity;
+  Recent seen;
+};
+
+// per-lane partial of one staged row (lane-permuted layout: group g of V chunks at float-V index g*32 + lane)
+template <int C>
+__device__ __forceinline__ float staged_partial(const float (&q)[C], const float* row, int lane) {
+  constexpr int V = RowRegs<C>::V;
+  float acc = 0.0f;
+#pragma unroll
+  for (int g = 0; g < C / V; ++g) {
+    if constexpr (V == 4) {
+      float4 v = reinterpret_cast<const float4*>(row)[g * 32 + lane];
+      float d;
+      d = __fsub_rn(q[4 * g + 0], v.x), acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(q[4 * g + 1], v.y), acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(q[4 * g + 2], v.z), acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(q[4 * g + 3], v.w), acc = __fmaf_rn(d, d, acc);
+    } else if constexpr (V == 2) {
+      float2 v = reinterpret_cast<const float2*>(row)[g * 32 + lane];
+      float d;
+      d = __fsub_rn(q[2 * g + 0], v.x), acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(q[2 * g + 1], v.y), acc = __fmaf_rn(d, d, acc);
+    } else {
+      float d = __fsub_rn(q[g], row[g * 32 + lane]);
+      acc = __fmaf_rn(d, d, acc);
+    }
+  }
+  return acc;
+}
+
+// Evaluate the ids flagged new (lane j holds nb) and apply them to the list in lane order (= adjacency-list order,
+// core.rs:646-667).  `adj_prefetch` = base of the level-0 adjacency rows (or null) for the L2 prefetch of admitted ids.
+template <int EFR, int C, int S>
+__device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S>& w, uint32_t nb, uint32_t newmask, int ef,
+                                               CandList<EFR>& L, const uint32_t* adj_prefetch, int lane) {
+  constexpr uint32_t RB = Warp2<C, S>::kRowBytes;
+  const int n_new = __popc(newmask);
+  const int rank = __popc(newmask & ((1u << lane) - 1u));
+  const bool mine_new = (newmask >> lane) & 1u;
+  for (int base = 0; base < n_new; base += S) {
+    const int nr = min(S, n_new - base);
+    __syncwarp();  // the previous round's reads of the stage and of ids[] are complete
+    if (lane == 0) mbar_expect_tx(w.bar, (uint32_t)nr * RB);
+    __syncwarp();
+    if (mine_new && rank >= base && rank < base + nr) {
+      w.ids[rank - base] = nb;
+      bulk_g2s(w.stage_s + (uint32_t)(rank - base) * RB, g.vecs + (size_t)nb * (32 * C), RB, w.bar);
+    }
+    mbar_wait(w.bar, w.parity);
+    w.parity ^= 1u;
+    __syncwarp();
+    float acc[S];
+    const float* st = reinterpret_cast<const float*>(w.stage);
+#pragma unroll
+    for (int r = 0; r < S; ++r) acc[r] = (r < nr) ? staged_partial<C>(w.q, st + (size_t)r * (32 * C), lane) : 0.0f;
+    const float s = reduce_rows<S>(acc, lane);
+    const uint32_t id = (lane < nr) ? w.ids[lane] : kEmpty;
+    uint32_t cand = __ballot_sync(kFull, lane < nr && L.admits(s, ef));
+    while (cand) {
+      const int j = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float sj = __shfl_sync(kFull, s, j);
+      const uint32_t idj = __shfl_sync(kFull, id, j);
+      if (L.admits(sj, ef) && !list_has<EFR>(L, idj)) {          // core.rs:657 (threshold re-read per neighbour)
+        L.insert(sj, idj, ef, lane);                             // core.rs:658-664
+        if (adj_prefetch && lane < (int)(g.W / 32)) prefetch_l2(adj_prefetch + (size_t)idj * g.W + lane * 32);
+      }
+    }
+  }
+}
+
+template <int EFR, int C, int S>
+__device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S>& w, uint32_t nb, int ef, CandList<EFR>& L,
+                                              Counters& cnt, const uint32_t* adj_prefetch, int lane) {
+  const bool valid = nb != kEmpty;
+  const uint32_t vmask = __ballot_sync(kFull, valid);
+  if (!vmask) return;
+  cnt.n_adj += __popc(vmask);                                    // core.rs:646
+  const bool is_new = valid && w.seen.test_and_set(nb);          // core.rs:648-649 (ids of one list are distinct)
+  const uint32_t newmask = __ballot_sync(kFull, is_new);
+  if (!newmask) return;
+  cnt.n_dist += __popc(newmask);                                 // core.rs:652-656
+  eval_and_admit<EFR, C, S>(g, w, nb, newmask, ef, L, adj_prefetch, lane);
+}
+
+// core.rs:607-675
+template <int EFR, int C, int S>
+__device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S>& w, uint32_t ep, int ef, uint32_t level,
+                                              CandList<EFR>& L, Counters& cnt, int lane) {
+  w.seen.clear(lane);
+  L.init();
+  const uint32_t* adj_prefetch = (level == 0 && ef > 1) ? g.adj0 : nullptr;
+  {
+    const uint32_t nb = lane == 0 ? ep : kEmpty;                 // core.rs:617-628
+    if (lane == 0) w.seen.test_and_set(ep);
+    cnt.n_dist += 1;
+    eval_and_admit<EFR, C, S>(g, w, nb, 1u, ef, L, adj_prefetch, lane);
+  }
+  for (;;) {
+    const int pos = L.first_unexpanded();                        // core.rs:631-638
+    if (pos < 0) break;
+    uint32_t cid;
+    float cs;
+    L.get(pos, lane, true, cid, cs);
+    cnt.n_hops += 1;
+    uint32_t* ovf;
+    const uint32_t* row = row_ptr(g, cid, level, &ovf);          // core.rs:642-645
+    if (!row) continue;
+    bool more = true;
+    for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
+      const uint32_t nb = row[c * 32 + lane];
+      more = __shfl_sync(kFull, nb, 31) != kEmpty;               // rows are compact: an empty tail ends the list
+      expand_chunk2<EFR, C, S>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
+    }
+    if (more) {                                                  // overflow rows (degree is unbounded); rare
+      uint32_t link = *ovf;
+      while (link != kEmpty) {
+        uint32_t nb = g.pool[(size_t)link * 32 + lane];
+        link = __shfl_sync(kFull, nb, 31);
+        if (lane == 31) nb = kEmpty;
+        expand_chunk2<EFR, C, S>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
+      }
+    }
+  }
+}
+
+// shared memory per warp (bytes), 128-byte aligned pieces: stage | visited | ids | mbarrier
+__host__ __device__ inline size_t warp2_smem_bytes(uint32_t dim, int S, uint32_t vis_slots) {
+  return (size_t)S * dim * 4 + (size_t)vis_slots * 4 + 128 + 128;
+}
+
+// core.rs:477-486, 865-892
+template <int EFR, int C, int S>
+__global__ void __launch_bounds__(256) search_knn2_kernel(Graph g, SearchArgs a) {
+  extern __shared__ __align__(128) unsigned char smem2[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  unsigned char* base = smem2 + (size_t)warp * warp2_smem_bytes(32 * C, S, a.vis_slots);
+  Warp2<C, S> w;
+  w.stage = reinterpret_cast<const float4*>(base);
+  w.stage_s = smem_u32(base);
+  w.seen.tab = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128);
+  w.seen.n4 = a.vis_slots / 4;
+  w.seen.shift = 32 - (31 - __clz(a.vis_slots));
+  w.ids = w.seen.tab + a.vis_slots;
+  w.bar = smem_u32(w.ids + 32);
+  w.parity = 0;
+  if (lane == 0) mbar_init(w.bar, 1);
+  __syncwarp();
+
+  CandList<EFR> L;
+  uint32_t evals = 0;
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(a.work_counter, 1u);
+    qi = __shfl_sync(kFull, qi, 0);
+    if (qi >= a.nq) break;
+    Counters cnt = {0, 0, 0};
+    const float* qn = a.queries + (size_t)qi * (32 * C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) w.q[c] = qn[32 * c + lane];
+    const int32_t entry = g.meta[kMetaEntry];
+    uint32_t n_out = 0;
+    if (entry >= 0) {                                            // core.rs:481-483
+      uint32_t ep = (uint32_t)entry;
+      for (int lc = g.meta[kMetaMaxLayer]; lc >= 0; --lc) {      // core.rs:869-876
+        search_layer2<EFR, C, S>(g, w, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, cnt, lane);
+        float s;
+        if (lc > 0) L.get(0, lane, false, ep, s);
+      }
+      n_out = min((uint32_t)L.len, a.k);                         // core.rs:879
+    }
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) {                              // core.rs:878-891 nearest-first
+      uint32_t e = r * 32 + lane;
+      if (e < a.k) {
+        bool have = e < n_out;
+        a.ids[(size_t)qi * a.k + e] = have ? (L.id[r] & ~kExpanded) : kEmpty;
+        a.sims[(size_t)qi * a.k + e] = have ? L.sim[r] : -CUDART_INF_F;
+      }
+    }
+    for (uint32_t e = EFR * 32 + lane; e < a.k; e += 32) {
+      a.ids[(size_t)qi * a.k + e] = kEmpty;
+      a.sims[(size_t)qi * a.k + e] = -CUDART_INF_F;
+    }
+    if (lane == 0) {
+      a.counts[qi] = n_out;
+      if (a.stats) {
+        a.stats[(size_t)qi * 4 + 0] = cnt.n_dist;                // evaluations performed (>= the reference's count)
+        a.stats[(size_t)qi * 4 + 1] = cnt.n_adj;
+        a.stats[(size_t)qi * 4 + 2] = cnt.n_hops;
+        a.stats[(size_t)qi * 4 + 3] = 4u;                        // bit2: lossy visited table (n_dist may exceed the reference's)
+      }
+    }
+    evals += cnt.n_dist;
+  }
+  if (lane == 0 && a.retry_count) atomicAdd(a.retry_count + 1, evals);  // ctl[3]: evaluations of the launch (low 32 bits)
+}
+
+}  // namespace hnsw

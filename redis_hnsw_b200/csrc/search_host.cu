@@ -65,6 +65,9 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   if (ef == 0) ef = ef_construction;  // core.rs:485
   const int efr = efr_for(ef);
   if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
+  if (staged_kind && opt_search_impl != 1 && (opt_search_impl == 2 || !d_stats))
+    return search_device2(nq, d_q, k, ef, efr, d_ids, d_sims, d_counts, d_stats, s);
   if (!h_retry_seen) {
     cudaError_t e = cudaHostAlloc((void**)&h_retry_seen, 16, cudaHostAllocDefault);
     if (e != cudaSuccess) return cuda_fail(e, "pinned alloc");
@@ -129,6 +132,49 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   e = cudaMemcpyAsync(h_retry_seen, ctl + 2, 4, cudaMemcpyDeviceToHost, s);
   if (e != cudaSuccess) return cuda_fail(e, "retry feedback");
   h_retry_seen[1] = (uint32_t)nq;
+  return HNSW_OK;
+}
+
+// TMA-staged kernel (search2.cuh): no retry pass (its visited table cannot overflow)
+int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef, int efr, uint32_t* d_ids, float* d_sims,
+                          uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s) {
+  int S = opt_stage_rows;
+  if (!S) {
+    uint32_t rows = 16384u / (dim * 4);  // about 16 KB of rows in flight per warp
+    S = rows >= 32 ? 32 : (rows >= 16 ? 16 : 8);
+  }
+  const uint32_t slots = opt_recent_slots ? opt_recent_slots : 1024;
+  const size_t per_warp = warp2_smem_bytes(dim, S, slots);
+  int block = opt_block ? opt_block : 128;
+  while (block > 32 && (size_t)(block / 32) * per_warp > max_smem) block /= 2;
+  const int warps = block / 32;
+  const size_t smem = (size_t)warps * per_warp;
+  if (smem > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the staged search kernel");
+  const int id = S == 32 ? kKernSearch2S32 : (S == 16 ? kKernSearch2S16 : kKernSearch2S8);
+  int occ = occupancy(kind, id, efr, block, smem);
+  if (occ < 1) return fail(HNSW_ERR_CUDA, "staged search kernel cannot be resident (block %d, smem %zu)", block, smem);
+  if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
+  const int grid = (int)std::min<uint64_t>((uint64_t)num_sms * occ, (nq + warps - 1) / warps);
+  int rc = ensure_scratch(s_ctl, 64 + (size_t)nq * 4);
+  if (rc) return rc;
+  uint32_t* ctl = (uint32_t*)s_ctl.p;
+  cudaError_t e = cudaMemsetAsync(ctl, 0, 64, s);
+  if (e != cudaSuccess) return cuda_fail(e, "search ctl memset");
+  SearchArgs a{};
+  a.queries = d_q;
+  a.nq = (uint32_t)nq;
+  a.k = k;
+  a.ef = ef;
+  a.ids = d_ids;
+  a.sims = d_sims;
+  a.counts = d_counts;
+  a.stats = d_stats;
+  a.work_counter = ctl + 0;
+  a.retry_count = ctl + 2;
+  a.vis_slots = slots;
+  LaunchCfg c{grid, block, smem, s};
+  e = run(kind, id, efr, c, g, &a);
+  if (e != cudaSuccess) return cuda_fail(e, "search_knn2 launch");
   return HNSW_OK;
 }
 

@@ -22,6 +22,29 @@ def test_search_parity(name, efs):
         assert_search_parity(dev, c["oracle"], c["q"], 10, ef)
 
 
+@pytest.mark.parametrize("name", ["cfg1_10k_d32_m5", "d128_m16", "d768_m32"])
+def test_staged_kernel_counters_and_options(name):
+    """search2.cuh: hops and adjacency ids equal the oracle's; its lossy visited table may re-evaluate a node, so
+    distance evaluations are >= the oracle's (and close); stage size / table size do not change results."""
+    c = case(name)
+    dev = device_index(name)
+    q = c["q"][:300]
+    oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=64)
+    ok = ost[:, 3] == 0
+    for rows, slots in ((0, 0), (8, 64), (16, 256), (32, 4096)):
+        dev.set_option("search_impl", 2)
+        dev.set_option("stage_rows", rows)
+        dev.set_option("recent_slots", slots)
+        ids, sims, counts, st = dev.search_batch(q, 10, ef=64, stats=True)
+        assert np.all(st[:, 3] == 4)
+        assert np.array_equal(ids[ok], oids[ok]) and np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
+        assert np.array_equal(counts, ocounts)
+        assert np.array_equal(st[ok, 1:3].astype(np.uint64), ost[ok, 1:3])
+        assert np.all(st[ok, 0] >= ost[ok, 0])
+        if slots == 0:
+            assert st[ok, 0].sum() <= 1.5 * ost[ok, 0].sum()
+
+
 def test_default_ef_is_ef_construction():
     """core.rs:485: search_knn always searches with ef = ef_construction."""
     c = case("cfg1_10k_d32_m5")
