@@ -630,11 +630,14 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
     if (value < 0 || value > 2) return fail(HNSW_ERR_INVALID, "search_impl must be 0 (auto), 1 or 2");
     ix.opt_search_impl = (int)value;
   } else if (n == "stage_rows") {
-    if (value != 0 && value != 8 && value != 16 && value != 32) return fail(HNSW_ERR_INVALID, "stage_rows must be 0, 8, 16 or 32");
+    if (value != 0 && value != 4 && value != 8 && value != 16 && value != 32) return fail(HNSW_ERR_INVALID, "stage_rows must be 0, 4, 8, 16 or 32");
     ix.opt_stage_rows = (int)value;
   } else if (n == "recent_slots") {
     if (value != 0 && (value < 64 || (value & (value - 1)))) return fail(HNSW_ERR_INVALID, "recent_slots must be 0 or a power of two >= 64");
     ix.opt_recent_slots = (uint32_t)value;
+  } else if (n == "recent_tag") {
+    if (value != 0 && value != 32) return fail(HNSW_ERR_INVALID, "recent_tag must be 0 (auto) or 32");
+    ix.opt_recent_tag = (int)value;
   } else if (n == "build_batch") {
     if (value < 1) return fail(HNSW_ERR_INVALID, "build_batch must be >= 1");
     ix.opt_build_batch = (uint32_t)value;

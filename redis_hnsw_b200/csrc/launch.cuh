@@ -34,10 +34,10 @@ enum KernelId : int {
   kKernBuildSearchGlobal = 4,
   kKernBuildReprune = 5,
   kKernExact = 6,
-  kKernSearch2S8 = 7,    // search_knn2_kernel (TMA-staged rows), 8 / 16 / 32 rows per stage
-  kKernSearch2S16 = 8,
-  kKernSearch2S32 = 9,
+  // search_knn2_kernel (TMA-staged rows): id = kKernSearch2 + 2 * log2(S / 4) + (16-bit visited tags ? 1 : 0)
+  kKernSearch2 = 16,
 };
+inline int search2_id(int S, bool tag16) { return kKernSearch2 + 2 * (S == 4 ? 0 : S == 8 ? 1 : S == 16 ? 2 : 3) + (tag16 ? 1 : 0); }
 
 // kernel arguments are passed type-erased so that one entry point per kind serves every kernel
 struct KernelArgs {
@@ -91,9 +91,14 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
   }
   if constexpr (Dist::kStaged) {
     switch (id) {
-      case kKernSearch2S8: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8>), SearchArgs)
-      case kKernSearch2S16: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16>), SearchArgs)
-      case kKernSearch2S32: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32>), SearchArgs)
+      case kKernSearch2 + 0: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, uint32_t>), SearchArgs)
+      case kKernSearch2 + 1: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, uint16_t>), SearchArgs)
+      case kKernSearch2 + 2: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, uint32_t>), SearchArgs)
+      case kKernSearch2 + 3: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, uint16_t>), SearchArgs)
+      case kKernSearch2 + 4: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint32_t>), SearchArgs)
+      case kKernSearch2 + 5: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint16_t>), SearchArgs)
+      case kKernSearch2 + 6: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint32_t>), SearchArgs)
+      case kKernSearch2 + 7: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t>), SearchArgs)
     }
   }
 #undef HNSW_RUN

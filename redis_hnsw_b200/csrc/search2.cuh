@@ -93,21 +93,37 @@ __device__ __forceinline__ float reduce_rows(float (&acc)[S], int lane) {
 
 // ---------------------------------------------------------------- lossy exact-tag visited table
 
+// Direct-mapped table of the most recently evaluated ids.  An entry identifies its id EXACTLY (never a false
+// "seen"); a conflicting id simply replaces the older one (a false "new" costs one redundant evaluation).
+//   T = uint32_t : the entry is the id itself.
+//   T = uint16_t : f(id) = id * odd mod 2^(B+15) is a bijection on ids < 2^(B+15) (B = log2 slots); slot = the top B
+//                  bits of f, entry = 0x8000 | low 15 bits of f, so (slot, entry) still determines the id.  Half the
+//                  shared memory per slot; the host picks it only when every id is below 2^(B+15).
+template <class T>
 struct Recent {
-  uint32_t* tab;
-  uint32_t n4;  // slots / 4
-  int shift;    // 32 - log2(slots)
+  T* tab;
+  uint32_t n16;   // table bytes / 16
+  int bits;       // B = log2(slots)
   __device__ __forceinline__ void clear(int lane) {
-    uint4 e = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+    const uint32_t fill = sizeof(T) == 4 ? kEmpty : 0u;
+    uint4 e = make_uint4(fill, fill, fill, fill);
     uint4* t = reinterpret_cast<uint4*>(tab);
-    for (uint32_t i = lane; i < n4; i += 32) t[i] = e;
+    for (uint32_t i = lane; i < n16; i += 32) t[i] = e;
     __syncwarp();
   }
   // true if `nid` was NOT found (and is now remembered)
   __device__ __forceinline__ bool test_and_set(uint32_t nid) {
-    uint32_t slot = (nid * 2654435761u) >> shift;
-    if (tab[slot] == nid) return false;
-    tab[slot] = nid;
+    if constexpr (sizeof(T) == 4) {
+      uint32_t slot = (nid * 2654435761u) >> (32 - bits);
+      if (tab[slot] == nid) return false;
+      tab[slot] = nid;
+    } else {
+      uint32_t f = (nid * 2654435761u) & ((1u << (bits + 15)) - 1u);
+      uint32_t slot = f >> 15;
+      T tag = (T)(0x8000u | (f & 0x7FFFu));
+      if (tab[slot] == tag) return false;
+      tab[slot] = tag;
+    }
     return true;
   }
 };
@@ -122,7 +138,7 @@ __device__ __forceinline__ bool list_has(const CandList<EFR>& L, uint32_t x) {
 
 // ---------------------------------------------------------------- per-warp context
 
-template <int C, int S>
+template <int C, int S, class T>
 struct Warp2 {
   static constexpr uint32_t kRowBytes = 128u * C;
   float q[C];          // q[c] = query[32c + lane]
@@ -131,7 +147,7 @@ struct Warp2 {
   uint32_t* ids;       // [32] compacted neighbour ids of the round
   uint32_t bar;        // shared-space address of the mbarrier
   uint32_t parity;
-  Recent seen;
+  Recent<T> seen;
 };
 
 // per-lane partial of one staged row (lane-permuted layout: group g of V chunks at float-V index g*32 + lane)
@@ -163,10 +179,10 @@ __device__ __forceinline__ float staged_partial(const float (&q)[C], const float
 
 // Evaluate the ids flagged new (lane j holds nb) and apply them to the list in lane order (= adjacency-list order,
 // core.rs:646-667).  `adj_prefetch` = base of the level-0 adjacency rows (or null) for the L2 prefetch of admitted ids.
-template <int EFR, int C, int S>
-__device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S>& w, uint32_t nb, uint32_t newmask, int ef,
+template <int EFR, int C, int S, class T>
+__device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w, uint32_t nb, uint32_t newmask, int ef,
                                                CandList<EFR>& L, const uint32_t* adj_prefetch, int lane) {
-  constexpr uint32_t RB = Warp2<C, S>::kRowBytes;
+  constexpr uint32_t RB = Warp2<C, S, T>::kRowBytes;
   const int n_new = __popc(newmask);
   const int rank = __popc(newmask & ((1u << lane) - 1u));
   const bool mine_new = (newmask >> lane) & 1u;
@@ -202,8 +218,8 @@ __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S>& w, u
   }
 }
 
-template <int EFR, int C, int S>
-__device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S>& w, uint32_t nb, int ef, CandList<EFR>& L,
+template <int EFR, int C, int S, class T>
+__device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S, T>& w, uint32_t nb, int ef, CandList<EFR>& L,
                                               Counters& cnt, const uint32_t* adj_prefetch, int lane) {
   const bool valid = nb != kEmpty;
   const uint32_t vmask = __ballot_sync(kFull, valid);
@@ -213,12 +229,12 @@ __device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S>& w, ui
   const uint32_t newmask = __ballot_sync(kFull, is_new);
   if (!newmask) return;
   cnt.n_dist += __popc(newmask);                                 // core.rs:652-656
-  eval_and_admit<EFR, C, S>(g, w, nb, newmask, ef, L, adj_prefetch, lane);
+  eval_and_admit<EFR, C, S, T>(g, w, nb, newmask, ef, L, adj_prefetch, lane);
 }
 
 // core.rs:607-675
-template <int EFR, int C, int S>
-__device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S>& w, uint32_t ep, int ef, uint32_t level,
+template <int EFR, int C, int S, class T>
+__device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w, uint32_t ep, int ef, uint32_t level,
                                               CandList<EFR>& L, Counters& cnt, int lane) {
   w.seen.clear(lane);
   L.init();
@@ -227,7 +243,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S>& w, ui
     const uint32_t nb = lane == 0 ? ep : kEmpty;                 // core.rs:617-628
     if (lane == 0) w.seen.test_and_set(ep);
     cnt.n_dist += 1;
-    eval_and_admit<EFR, C, S>(g, w, nb, 1u, ef, L, adj_prefetch, lane);
+    eval_and_admit<EFR, C, S, T>(g, w, nb, 1u, ef, L, adj_prefetch, lane);
   }
   for (;;) {
     const int pos = L.first_unexpanded();                        // core.rs:631-638
@@ -243,7 +259,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S>& w, ui
     for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
       const uint32_t nb = row[c * 32 + lane];
       more = __shfl_sync(kFull, nb, 31) != kEmpty;               // rows are compact: an empty tail ends the list
-      expand_chunk2<EFR, C, S>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
+      expand_chunk2<EFR, C, S, T>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
     }
     if (more) {                                                  // overflow rows (degree is unbounded); rare
       uint32_t link = *ovf;
@@ -251,31 +267,32 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S>& w, ui
         uint32_t nb = g.pool[(size_t)link * 32 + lane];
         link = __shfl_sync(kFull, nb, 31);
         if (lane == 31) nb = kEmpty;
-        expand_chunk2<EFR, C, S>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
+        expand_chunk2<EFR, C, S, T>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
       }
     }
   }
 }
 
 // shared memory per warp (bytes), 128-byte aligned pieces: stage | visited | ids | mbarrier
-__host__ __device__ inline size_t warp2_smem_bytes(uint32_t dim, int S, uint32_t vis_slots) {
-  return (size_t)S * dim * 4 + (size_t)vis_slots * 4 + 128 + 128;
+__host__ __device__ inline size_t warp2_smem_bytes(uint32_t dim, int S, uint32_t vis_slots, uint32_t slot_bytes) {
+  return (size_t)S * dim * 4 + (((size_t)vis_slots * slot_bytes + 127) & ~(size_t)127) + 128 + 128;
 }
 
 // core.rs:477-486, 865-892
-template <int EFR, int C, int S>
+template <int EFR, int C, int S, class T>
 __global__ void __launch_bounds__(256) search_knn2_kernel(Graph g, SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem2[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  unsigned char* base = smem2 + (size_t)warp * warp2_smem_bytes(32 * C, S, a.vis_slots);
-  Warp2<C, S> w;
+  unsigned char* base = smem2 + (size_t)warp * warp2_smem_bytes(32 * C, S, a.vis_slots, sizeof(T));
+  Warp2<C, S, T> w;
   w.stage = reinterpret_cast<const float4*>(base);
   w.stage_s = smem_u32(base);
-  w.seen.tab = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128);
-  w.seen.n4 = a.vis_slots / 4;
-  w.seen.shift = 32 - (31 - __clz(a.vis_slots));
-  w.ids = w.seen.tab + a.vis_slots;
+  const uint32_t tab_bytes = (a.vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
+  w.seen.tab = reinterpret_cast<T*>(base + (size_t)S * C * 128);
+  w.seen.n16 = tab_bytes / 16;
+  w.seen.bits = 31 - __clz(a.vis_slots);
+  w.ids = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128 + tab_bytes);
   w.bar = smem_u32(w.ids + 32);
   w.parity = 0;
   if (lane == 0) mbar_init(w.bar, 1);
@@ -297,7 +314,7 @@ __global__ void __launch_bounds__(256) search_knn2_kernel(Graph g, SearchArgs a)
     if (entry >= 0) {                                            // core.rs:481-483
       uint32_t ep = (uint32_t)entry;
       for (int lc = g.meta[kMetaMaxLayer]; lc >= 0; --lc) {      // core.rs:869-876
-        search_layer2<EFR, C, S>(g, w, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, cnt, lane);
+        search_layer2<EFR, C, S, T>(g, w, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, cnt, lane);
         float s;
         if (lc > 0) L.get(0, lane, false, ep, s);
       }

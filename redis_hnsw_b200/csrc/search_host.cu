@@ -140,17 +140,23 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
                           uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s) {
   int S = opt_stage_rows;
   if (!S) {
-    uint32_t rows = 16384u / (dim * 4);  // about 16 KB of rows in flight per warp
-    S = rows >= 32 ? 32 : (rows >= 16 ? 16 : 8);
+    // about 4 KB of rows in flight per warp: on a B200 the kernel is occupancy-hungry (measured, profiles/), many
+    // warps with a small stage each beat few warps with a deep one
+    uint32_t rows = 4096u / (dim * 4);
+    S = rows >= 32 ? 32 : (rows >= 16 ? 16 : (rows >= 8 ? 8 : 4));
   }
   const uint32_t slots = opt_recent_slots ? opt_recent_slots : 1024;
-  const size_t per_warp = warp2_smem_bytes(dim, S, slots);
-  int block = opt_block ? opt_block : 128;
+  int slot_bits = 0;
+  while ((1u << slot_bits) < slots) ++slot_bits;
+  // 16-bit tags identify an id exactly only below 2^(log2(slots) + 15)
+  const bool tag16 = opt_recent_tag != 32 && slot_bits + 15 < 32 && n_ids <= (1ull << (slot_bits + 15));
+  const size_t per_warp = warp2_smem_bytes(dim, S, slots, tag16 ? 2 : 4);
+  int block = opt_block ? opt_block : 64;
   while (block > 32 && (size_t)(block / 32) * per_warp > max_smem) block /= 2;
   const int warps = block / 32;
   const size_t smem = (size_t)warps * per_warp;
   if (smem > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the staged search kernel");
-  const int id = S == 32 ? kKernSearch2S32 : (S == 16 ? kKernSearch2S16 : kKernSearch2S8);
+  const int id = search2_id(S, tag16);
   int occ = occupancy(kind, id, efr, block, smem);
   if (occ < 1) return fail(HNSW_ERR_CUDA, "staged search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);

@@ -31,10 +31,11 @@ def test_staged_kernel_counters_and_options(name):
     q = c["q"][:300]
     oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=64)
     ok = ost[:, 3] == 0
-    for rows, slots in ((0, 0), (8, 64), (16, 256), (32, 4096)):
+    for rows, slots, tag in ((0, 0, 0), (4, 64, 0), (8, 64, 32), (16, 256, 0), (32, 4096, 32)):
         dev.set_option("search_impl", 2)
         dev.set_option("stage_rows", rows)
         dev.set_option("recent_slots", slots)
+        dev.set_option("recent_tag", tag)
         ids, sims, counts, st = dev.search_batch(q, 10, ef=64, stats=True)
         assert np.all(st[:, 3] == 4)
         assert np.array_equal(ids[ok], oids[ok]) and np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
