@@ -79,13 +79,6 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows)}
 
 
-class DevPtr:
-    """Zero-copy torch view of a raw device buffer (for the NCCL broadcast of the index)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def make_data(wl, nq_total):
     from redis_hnsw_b200 import data
 
@@ -113,19 +106,7 @@ def build_index(wl, x, levels, device, rank, world):
         dev.add_batch(x, levels, mode=r.BUILD_FAST)
         build_s = time.perf_counter() - t0
         log("built %d nodes in %.1f s (%.0f inserts/s) %s" % (n, build_s, n / build_s, dev.build_stats()))
-    if world > 1:
-        import torch.distributed as dist
-
-        lay = torch.from_numpy(dev.replica_layout().astype(np.int64)).cuda() if rank == 0 else torch.zeros(8, dtype=torch.int64, device="cuda")
-        dist.broadcast(lay, 0)
-        if rank != 0:
-            dev.prepare_replica(lay.cpu().numpy().astype(np.uint64))
-        for ptr, nbytes in dev.device_buffers():
-            if nbytes:
-                dist.broadcast(torch.as_tensor(DevPtr(ptr, nbytes), device="cuda"), 0)
-        torch.cuda.synchronize()
-        if rank != 0:
-            dev.adopt_replica()
+    r.sharding.replicate_index(dev, rank, world)   # one NCCL broadcast per device buffer
     return dev, build_s
 
 
