@@ -227,13 +227,16 @@ __device__ __forceinline__ bool expand_row(const Graph& g, const Dist& dist, uin
 
 // select_neighbors(e, N(e), cap, lc) as insert calls it (core.rs:544-568): on return L holds the top-`cap` of
 // N(e) ∪ N(N(e)) \ {e} by sim(e, .), nearest-first.  `old` = N_lc(e) (shared memory), `dist` holds e's vector.
+// `ignored` (kEmpty = none) is the node being deleted when delete_node_from_neighbors makes the call
+// (core.rs:853): never a candidate (core.rs:704-708, 728-731), but its row IS swept when it is a member of `old`.
 // Returns false if the visited table overflowed.
 template <int EFR, class Dist>
 __device__ __forceinline__ bool reprune_select(const Graph& g, const Dist& dist, uint32_t e, uint32_t level, int cap,
                                                const uint32_t* old, uint32_t n_old, CandList<EFR>& L, Visited& vis,
-                                               Counters& cnt, int lane) {
+                                               Counters& cnt, int lane, uint32_t ignored = kEmpty) {
   visited_clear(vis, lane);
   visited_insert(vis, e, lane == 0);  // e itself is never a candidate (core.rs:704, 728)
+  if (ignored != kEmpty) visited_insert(vis, ignored, lane == 0);
   L.init();
   for (uint32_t i = 0; i < n_old; i += 32) {  // econn: sims of the current neighbours (core.rs:549-557)
     uint32_t nb = (i + lane < n_old) ? old[i + lane] : kEmpty;
@@ -405,6 +408,113 @@ __global__ void __launch_bounds__(32) insert_exact_kernel(Graph g, ExactArgs a) 
     }
     __syncwarp();
     if (lane == 0) a.ctl[kCtlProgress] = it + 1;
+  }
+  if (lane == 0) {
+    a.ctl[kCtlDistEvals] += cnt.n_dist;
+    a.ctl[kCtlReprunes] += n_reprunes;
+    a.ctl[kCtlTouched] = n_touched;
+  }
+}
+
+// ---------------------------------------------------------------- delete_node (core.rs:414-475, 824-863)
+
+// One warp removes node a.first from the graph exactly as the reference does: for every level of the victim and every
+// neighbour n of the victim IN LIST ORDER (core.rs:829), n's whole list is re-selected with the victim ignored —
+// top-cap of N(n) ∪ N(N(n)) \ {n, victim}, whether or not n was over its cap (core.rs:846-853) — and applied through
+// update_node_connections (core.rs:856), whose removal of the victim from n's list is not mirrored (core.rs:810-813):
+// the victim's own lists stay intact while they are being walked and are cleared at the end.
+template <int EFR, class Dist>
+__global__ void __launch_bounds__(32) delete_exact_kernel(Graph g, ExactArgs a) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = lane_id();
+  // shared memory: vlist[lcap] | old[lcap] | keep_add[lcap + W] | rem[lcap] | edit[lcap] | query[dim] (if needed)
+  uint32_t* vlist = smem;
+  uint32_t* old = vlist + a.lcap;
+  uint32_t* keep_add = old + a.lcap;
+  uint32_t* rem = keep_add + a.lcap + g.W;
+  uint32_t* edit = rem + a.lcap;
+  float* smem_q = reinterpret_cast<float*>(edit + a.lcap);
+
+  Visited vis;
+  vis.tab = a.vis;
+  vis.mask = a.vis_slots - 1;
+  vis.shift = 32 - (31 - __clz(a.vis_slots));
+  vis.limit = a.vis_slots - a.vis_slots / 4;
+
+  Dist dist;
+  CandList<EFR> L;
+  Counters cnt = {0, 0, 0};
+  uint32_t n_touched = 0, n_reprunes = 0;
+  auto touch = [&](uint32_t id) {
+    if (a.touched) {
+      if (lane == 0 && n_touched < a.touched_cap) a.touched[n_touched] = id;
+      ++n_touched;
+    }
+  };
+  auto flag = [&](int err) {
+    if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)err);
+  };
+
+  const uint32_t victim = a.first;
+  const int top = g.level[victim];
+  bool ok = true;
+  for (int lc = 0; lc <= top && ok; ++lc) {                       // core.rs:434-440
+    const uint32_t cap = lc == 0 ? a.cap0 : a.capU;               // core.rs:846
+    uint32_t* vovf;
+    uint32_t* vrow = row_ptr(g, victim, (uint32_t)lc, &vovf);
+    if (!vrow) continue;
+    const uint32_t n_v = list_load(g, vrow, vovf, vlist, a.lcap, lane);
+    if (n_v == kEmpty) {
+      flag(kErrListTooLong);
+      ok = false;
+      break;
+    }
+    for (uint32_t i = 0; i < n_v && ok; ++i) {                    // core.rs:829 list order
+      const uint32_t n = vlist[i];
+      uint32_t* novf;
+      uint32_t* nrow = row_ptr(g, n, (uint32_t)lc, &novf);
+      if (!nrow) continue;
+      const uint32_t n_old = list_load(g, nrow, novf, old, a.lcap, lane);   // nconn (core.rs:834-844)
+      if (n_old == kEmpty) {
+        flag(kErrListTooLong);
+        ok = false;
+        break;
+      }
+      dist.load_query_slab(g, n, smem_q, lane);
+      ok = reprune_select<EFR, Dist>(g, dist, n, (uint32_t)lc, (int)cap, old, n_old, L, vis, cnt, lane, victim);  // :853
+      if (!ok) {
+        flag(kErrVisitedOverflow);
+        break;
+      }
+      ++n_reprunes;
+      uint32_t n_keep, n_add, n_rem;
+      reprune_delta<EFR>(L, old, n_old, keep_add, rem, n_keep, n_add, n_rem, lane);
+      // update_node_connections(n, new, nconn, lc, Some(victim))  core.rs:776-822
+      list_store(g, nrow, novf, keep_add, n_keep + n_add, lane);
+      touch(n);                                                   // core.rs:855, 787
+      for (uint32_t t = 0; t < n_add; ++t) {                      // core.rs:793-796
+        row_append_unique(g, keep_add[n_keep + t], (uint32_t)lc, n, edit, a.lcap, lane);
+        touch(keep_add[n_keep + t]);
+      }
+      for (uint32_t t = 0; t < n_keep; ++t) touch(keep_add[t]);
+      for (uint32_t t = 0; t < n_rem; ++t) {                      // core.rs:805-816
+        if (rem[t] == victim) continue;                           // core.rs:810-813: not mirrored, not reported
+        row_remove(g, rem[t], (uint32_t)lc, n, edit, a.lcap, lane);
+        touch(rem[t]);
+      }
+    }
+  }
+  if (ok) {
+    for (int lc = 0; lc <= top; ++lc) {                           // the node is dropped (core.rs:419)
+      uint32_t* vovf;
+      uint32_t* vrow = row_ptr(g, victim, (uint32_t)lc, &vovf);
+      if (vrow) list_store(g, vrow, vovf, vlist, 0, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      g.level[victim] = -1;
+      a.ctl[kCtlProgress] = 1;
+    }
   }
   if (lane == 0) {
     a.ctl[kCtlDistEvals] += cnt.n_dist;

@@ -297,6 +297,90 @@ int Index::add_fast(uint32_t first, uint32_t count) {
   return HNSW_OK;
 }
 
+// ---------------------------------------------------------------- delete_node (core.rs:414-475)
+
+int Index::delete_node(uint32_t id) {
+  if (id >= n_ids || h_level[id] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", id);  // core.rs:421
+  const int efr = build_efr(*this);
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
+  int rc = pull_meta();  // the device owns pool_used
+  if (rc) return rc;
+  const uint32_t lcap = list_capacity(g.W);
+  // every re-selection may append this node to up to `cap` other rows (core.rs:793-795)
+  if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)(h_level[id] + 1) * lcap * 2 + 1024))) return rc;
+  if (!exact_vis_slots) exact_vis_slots = next_pow2(std::max<uint64_t>(1u << 16, (uint64_t)ef_construction * 256));
+  const uint32_t touched_cap = 1u << 16;
+  if ((rc = ensure_scratch(s_bvis, (size_t)exact_vis_slots * 4))) return rc;
+  if ((rc = ensure_scratch(s_ctl, 64 + (size_t)kCtlWords * 4 + (size_t)touched_cap * 4))) return rc;
+  uint32_t* ctl = (uint32_t*)s_ctl.p;
+  cudaError_t e = cudaMemsetAsync(ctl, 0, (size_t)kCtlWords * 4, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "delete ctl memset");
+  ExactArgs a{};
+  a.first = id;
+  a.count = 1;
+  a.m = m;
+  a.cap0 = m_max_0;
+  a.capU = m_max;
+  a.efc = ef_construction;
+  a.lcap = lcap;
+  a.vis_slots = exact_vis_slots;
+  a.vis = (uint32_t*)s_bvis.p;
+  a.ctl = ctl;
+  a.touched = ctl + kCtlWords;
+  a.touched_cap = touched_cap;
+  size_t smem = (5 * (size_t)lcap + g.W) * 4 + (kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0);
+  LaunchCfg c{1, 32, smem, stream};
+  e = run(kind, kKernDelete, efr, c, g, &a);
+  if (e != cudaSuccess) return cuda_fail(e, "delete_exact launch");
+  uint32_t h[kCtlWords];
+  e = cudaMemcpyAsync(h, ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return cuda_fail(e, "delete_exact");
+  if ((rc = pull_meta())) return rc;
+  build_stats[2] += h[kCtlReprunes];
+  build_stats[3] += h[kCtlDistEvals];
+  uint32_t nt = std::min(h[kCtlTouched], touched_cap);
+  touched.resize(nt);
+  if (nt) {
+    e = cudaMemcpyAsync(touched.data(), a.touched, (size_t)nt * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return cuda_fail(e, "touched D2H");
+  }
+  std::sort(touched.begin(), touched.end());
+  touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+  if (device_error || h[kCtlProgress] != 1) {
+    int err = device_error;
+    device_error = 0;
+    push_meta();
+    return fail(HNSW_ERR_INVALID, "delete of node %u stopped part-way (device error flags 0x%x: %s)", id, err,
+                (err & kErrVisitedOverflow) ? "visited table overflow" : (err & kErrPoolExhausted) ? "overflow-row pool exhausted"
+                                                                                                    : "adjacency list too long");
+  }
+  h_level[id] = -1;  // leaves `nodes` and its layer set (core.rs:419, 426-430)
+  node_count -= 1;   // core.rs:424
+  if (entry == (int32_t)id) {  // core.rs:449-472
+    // The reference takes "the first element of a HashSet iterator" of the highest non-empty layer set
+    // (core.rs:453: not deterministic); like the oracle we take the smallest id listed in that layer.  A node is
+    // listed only in the layer of its own top level (core.rs:596).
+    int32_t new_ep = -1, ml = max_layer;
+    for (int lc = max_layer; lc >= 0; --lc) {
+      int64_t first = -1;
+      for (uint64_t i = 0; i < n_ids; ++i)
+        if (h_level[i] == lc) {
+          first = (int64_t)i;
+          break;
+        }
+      if (first >= 0) {
+        new_ep = (int32_t)first;
+        break;
+      }
+      if (ml > 0) ml -= 1;  // core.rs:460-463
+    }
+    if ((rc = set_entry(new_ep, ml))) return rc;
+  }
+  return HNSW_OK;
+}
+
 // ---------------------------------------------------------------- add_node (core.rs:383-412)
 
 int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id,
@@ -382,8 +466,7 @@ int hnsw_index_touched(hnsw_index_t* idx, uint32_t* ids, uint64_t cap, uint64_t*
 
 int hnsw_index_delete(hnsw_index_t* idx, uint32_t id) {
   IDX_OR_FAIL(idx)
-  (void)id;
-  return fail(HNSW_ERR_INVALID, "hnsw_index_delete: not implemented yet");
+  return ix.delete_node(id);
 }
 
 int hnsw_index_build_stats(hnsw_index_t* idx, uint64_t* out4) {

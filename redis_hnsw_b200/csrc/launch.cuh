@@ -34,6 +34,7 @@ enum KernelId : int {
   kKernBuildSearchGlobal = 4,
   kKernBuildReprune = 5,
   kKernExact = 6,
+  kKernDelete = 7,
   // search_knn2_kernel (TMA-staged rows): id = kKernSearch2 + 2 * log2(S / 4) + (16-bit visited tags ? 1 : 0)
   kKernSearch2 = 16,
 };
@@ -88,6 +89,7 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
     case kKernBuildSearchGlobal: HNSW_RUN((build_search_kernel<EFR, Dist, false>), FastArgs)
     case kKernBuildReprune: HNSW_RUN((build_reprune_kernel<EFR, Dist>), FastArgs)
     case kKernExact: HNSW_RUN((insert_exact_kernel<EFR, Dist>), ExactArgs)
+    case kKernDelete: HNSW_RUN((delete_exact_kernel<EFR, Dist>), ExactArgs)
   }
   if constexpr (Dist::kStaged) {
     switch (id) {
