@@ -336,8 +336,17 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_ms = float(np.mean(step_ms))
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of one launch from the committed ncu --set full capture of this workload (profiles/traffic.json)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
+        if tr and tr["ef"] == ef:
+            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * nq / tr["queries_per_launch"]
+            traffic_src = tr["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel": "search_knn2_kernel (one launch per step; duration = CUDA events around the step on the launch stream)",
                 "alg_bytes_per_query": alg_bytes / nq, "dist_evals_per_query": n_dist / nq, "adj_ids_per_query": n_adj / nq,
