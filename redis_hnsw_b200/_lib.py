@@ -6,6 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libhnsw_b200.so")
+REDIS_MODULE_PATH = os.path.join(_HERE, "libredis_hnsw_b200.so")  # redis-server --loadmodule <this>
 
 HNSW_OK = 0
 ERR_DIM_MISMATCH, ERR_EXISTS, ERR_NOT_FOUND, ERR_INVALID, ERR_CUDA, ERR_OOM = 1, 2, 3, 4, 5, 6
@@ -65,6 +66,8 @@ _lib = None
 def build(jobs=8):
     """Compile libhnsw_b200.so for sm_100a with the in-tree Makefile (nvcc cross-compiles without a GPU)."""
     subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j%d" % jobs], stdout=subprocess.DEVNULL)
+    # the Redis module (host side, plain C++ over the C ABI) and the fake module host the tests drive it with
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc", "redis")], stdout=subprocess.DEVNULL)
     return SO_PATH
 
 

@@ -202,10 +202,51 @@ __device__ __forceinline__ void row_remove(const Graph& g, uint32_t node, uint32
 
 // ---------------------------------------------------------------- re-selection of an over-full row
 
-// walk the adjacency list of (node, level) chunk by chunk through expand_chunk
+// is `x` (warp-uniform) one of the entries of L?
+template <int EFR>
+__device__ __forceinline__ bool cand_contains(const CandList<EFR>& L, uint32_t x) {
+  bool hit = false;
+#pragma unroll
+  for (int r = 0; r < EFR; ++r) hit |= __any_sync(kFull, (L.id[r] & ~kExpanded) == x && L.id[r] != kEmpty);
+  return hit;
+}
+
+// expand_chunk with a LOSSY visited table (direct-mapped, most recent id per slot): a hit proves "already
+// evaluated", a conflict forgets the older id.  Used by the batched builder's re-selection, whose 2-hop sweeps
+// (|N(e)| * degree ids) would need a very large exact table for big m: a forgotten id is evaluated again and the
+// membership test below keeps it from entering the list twice, so the selected set is the same top-cap set.
+// `skip_a` / `skip_b` (kEmpty = none) are never candidates (the node itself and the ignored node, core.rs:704-708).
 template <int EFR, class Dist>
+__device__ __forceinline__ void expand_chunk_lossy(const Graph& g, const Dist& dist, uint32_t nb, int ef, CandList<EFR>& L,
+                                                   Visited& vis, Counters& cnt, uint32_t skip_a, uint32_t skip_b, int lane) {
+  bool valid = nb != kEmpty && nb != skip_a && nb != skip_b;
+  if (!__any_sync(kFull, valid)) return;
+  bool is_new = false;
+  if (valid) {
+    uint32_t slot = (nb * 2654435761u) >> vis.shift;
+    is_new = vis.tab[slot] != nb;
+    if (is_new) vis.tab[slot] = nb;
+  }
+  __syncwarp();
+  uint32_t newmask = __ballot_sync(kFull, is_new);
+  if (!newmask) return;
+  cnt.n_dist += __popc(newmask);
+  float mine = dist.batch(g, nb, newmask, lane);
+  uint32_t cand = __ballot_sync(kFull, is_new && L.admits(mine, ef));
+  while (cand) {
+    int j = __ffs(cand) - 1;
+    cand &= cand - 1;
+    float s = __shfl_sync(kFull, mine, j);
+    uint32_t nid = __shfl_sync(kFull, nb, j);
+    if (L.admits(s, ef) && !cand_contains<EFR>(L, nid)) L.insert(s, nid, ef, lane);
+  }
+}
+
+// walk the adjacency list of (node, level) chunk by chunk through expand_chunk
+template <int EFR, class Dist, bool LOSSY = false>
 __device__ __forceinline__ bool expand_row(const Graph& g, const Dist& dist, uint32_t node, uint32_t level, int ef,
-                                           CandList<EFR>& L, Visited& vis, Counters& cnt, int lane) {
+                                           CandList<EFR>& L, Visited& vis, Counters& cnt, int lane,
+                                           uint32_t skip_a = kEmpty, uint32_t skip_b = kEmpty) {
   uint32_t* ovf;
   const uint32_t* row = row_ptr(g, node, level, &ovf);
   if (!row) return true;
@@ -214,13 +255,15 @@ __device__ __forceinline__ bool expand_row(const Graph& g, const Dist& dist, uin
   for (uint32_t w = 0; w < g.W / 32 && more; ++w) {
     uint32_t nb = row[w * 32 + lane];
     more = __shfl_sync(kFull, nb, 31) != kEmpty;
-    if (!expand_chunk<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, lane)) return false;
+    if constexpr (LOSSY) expand_chunk_lossy<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, skip_a, skip_b, lane);
+    else if (!expand_chunk<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, lane)) return false;
   }
   while (more && link != kEmpty) {
     uint32_t nb = g.pool[(size_t)link * 32 + lane];
     link = __shfl_sync(kFull, nb, 31);
     if (lane == 31) nb = kEmpty;
-    if (!expand_chunk<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, lane)) return false;
+    if constexpr (LOSSY) expand_chunk_lossy<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, skip_a, skip_b, lane);
+    else if (!expand_chunk<EFR, Dist>(g, dist, nb, ef, L, vis, cnt, lane)) return false;
   }
   return true;
 }
@@ -229,31 +272,26 @@ __device__ __forceinline__ bool expand_row(const Graph& g, const Dist& dist, uin
 // N(e) ∪ N(N(e)) \ {e} by sim(e, .), nearest-first.  `old` = N_lc(e) (shared memory), `dist` holds e's vector.
 // `ignored` (kEmpty = none) is the node being deleted when delete_node_from_neighbors makes the call
 // (core.rs:853): never a candidate (core.rs:704-708, 728-731), but its row IS swept when it is a member of `old`.
-// Returns false if the visited table overflowed.
-template <int EFR, class Dist>
+// LOSSY = false: exact visited set, returns false if the table overflowed.  LOSSY = true: direct-mapped table
+// (see expand_chunk_lossy), never fails.
+template <int EFR, class Dist, bool LOSSY = false>
 __device__ __forceinline__ bool reprune_select(const Graph& g, const Dist& dist, uint32_t e, uint32_t level, int cap,
                                                const uint32_t* old, uint32_t n_old, CandList<EFR>& L, Visited& vis,
                                                Counters& cnt, int lane, uint32_t ignored = kEmpty) {
   visited_clear(vis, lane);
-  visited_insert(vis, e, lane == 0);  // e itself is never a candidate (core.rs:704, 728)
-  if (ignored != kEmpty) visited_insert(vis, ignored, lane == 0);
+  if constexpr (!LOSSY) {
+    visited_insert(vis, e, lane == 0);  // e itself is never a candidate (core.rs:704, 728)
+    if (ignored != kEmpty) visited_insert(vis, ignored, lane == 0);
+  }
   L.init();
   for (uint32_t i = 0; i < n_old; i += 32) {  // econn: sims of the current neighbours (core.rs:549-557)
     uint32_t nb = (i + lane < n_old) ? old[i + lane] : kEmpty;
-    if (!expand_chunk<EFR, Dist>(g, dist, nb, cap, L, vis, cnt, lane)) return false;
+    if constexpr (LOSSY) expand_chunk_lossy<EFR, Dist>(g, dist, nb, cap, L, vis, cnt, e, ignored, lane);
+    else if (!expand_chunk<EFR, Dist>(g, dist, nb, cap, L, vis, cnt, lane)) return false;
   }
   for (uint32_t j = 0; j < n_old; ++j)        // extend_candidates (core.rs:698-721)
-    if (!expand_row<EFR, Dist>(g, dist, old[j], level, cap, L, vis, cnt, lane)) return false;
+    if (!expand_row<EFR, Dist, LOSSY>(g, dist, old[j], level, cap, L, vis, cnt, lane, e, ignored)) return false;
   return true;
-}
-
-// is `x` (warp-uniform) one of the entries of L?
-template <int EFR>
-__device__ __forceinline__ bool cand_contains(const CandList<EFR>& L, uint32_t x) {
-  bool hit = false;
-#pragma unroll
-  for (int r = 0; r < EFR; ++r) hit |= __any_sync(kFull, (L.id[r] & ~kExpanded) == x && L.id[r] != kEmpty);
-  return hit;
 }
 
 // Split the outcome of a re-selection against the old list:
@@ -700,7 +738,7 @@ __global__ void __launch_bounds__(256) build_reprune_kernel(Graph g, FastArgs a)
     bool ok = n_old != kEmpty;
     if (ok) {
       dist.load_query_slab(g, e, smem_q, lane);
-      ok = reprune_select<EFR, Dist>(g, dist, e, lc, (int)cap, old, n_old, L, vis, cnt, lane);
+      ok = reprune_select<EFR, Dist, true>(g, dist, e, lc, (int)cap, old, n_old, L, vis, cnt, lane);
     }
     if (!ok) {
       if (lane == 0) a.wl_len[2 * w] = 0, a.wl_len[2 * w + 1] = kEmpty;

@@ -44,7 +44,10 @@ int Index::set_entry(int32_t entry_, int32_t max_layer_) {
   return HNSW_OK;
 }
 
-static uint32_t list_capacity(uint32_t W) { return std::max<uint32_t>(256, 2 * W); }
+// Ids a list edit buffer holds.  Degree is unbounded in the reference (core.rs:793-795 appends back-edges without a
+// cap check) and the batched builder applies a whole batch of such appends before a hub row is re-selected: rows of
+// 230+ ids were measured at 70K x 768-d, M=32 (cap 64), so the buffers are sized well past the cap.
+static uint32_t list_capacity(uint32_t W) { return std::max<uint32_t>(512, 16 * W); }
 
 // list registers: the candidate list must hold ef_construction entries (search) and m_max_0 entries (re-selection)
 static int build_efr(const Index& ix) { return std::max(efr_for(ix.ef_construction), efr_for(ix.m_max_0)); }
@@ -225,6 +228,7 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   // K3
   {
     const uint32_t cap = m_max_0;
+    // lossy direct-mapped table (expand_chunk_lossy): any size is correct, a larger one saves re-evaluations
     const uint32_t rslots = next_pow2(std::max<uint64_t>(1024, (uint64_t)cap * 64));
     FastArgs a3 = a;
     a3.vis_slots = rslots;

@@ -1,0 +1,257 @@
+// NamedIndex: the reference's Index<f32,f32> interface (src/hnsw/core.rs) over the C ABI.  See named_index.hpp.
+#include "named_index.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace hnswhost {
+
+static std::string last_error() {
+  const char* e = hnsw_last_error();
+  return e ? std::string(e) : std::string("unknown error");
+}
+
+void NamedIndex::check(int rc) const {
+  if (rc != HNSW_OK) throw HNSWError(last_error(), rc);
+}
+
+// Rust's `{:?}` of a &str: quoted, with ", \ and control characters escaped (core.rs:408,421 format names this way)
+static std::string rust_debug_str(const std::string& s) {
+  std::string o = "\"";
+  for (char c : s) {
+    switch (c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\r': o += "\\r"; break;
+      case '\t': o += "\\t"; break;
+      default: o += c;
+    }
+  }
+  return o + "\"";
+}
+
+NamedIndex::NamedIndex(const std::string& name, uint64_t data_dim, uint64_t m, uint64_t ef_construction, int device)
+    : name_(name), dim_((uint32_t)data_dim) {
+  if (data_dim == 0 || data_dim > 0xFFFFFFFFull || m > 0xFFFFFFFFull || ef_construction > 0xFFFFFFFFull)
+    throw HNSWError("index parameters out of range");
+  int rc = hnsw_index_create((uint32_t)data_dim, (uint32_t)m, (uint32_t)ef_construction, device, &h_);
+  if (rc != HNSW_OK) {
+    h_ = nullptr;
+    throw HNSWError(last_error(), rc);
+  }
+}
+
+NamedIndex::~NamedIndex() {
+  if (h_) hnsw_index_destroy(h_);
+}
+
+hnsw_params_t NamedIndex::params() const {
+  hnsw_params_t p{};
+  check(hnsw_index_params(h_, &p));
+  return p;
+}
+
+std::optional<std::string> NamedIndex::enterpoint() const {
+  hnsw_params_t p = params();
+  if (p.enterpoint == HNSW_NO_NODE) return std::nullopt;
+  return names_[p.enterpoint];
+}
+
+std::vector<std::string> NamedIndex::touched_names() const {
+  uint64_t n = 0;
+  check(hnsw_index_touched(h_, nullptr, 0, &n));
+  std::vector<uint32_t> ids(n);
+  if (n) check(hnsw_index_touched(h_, ids.data(), n, &n));
+  std::vector<std::string> out;
+  out.reserve(ids.size());
+  for (uint32_t t : ids)
+    if (t < names_.size() && alive_[t]) out.push_back(names_[t]);
+  return out;
+}
+
+void NamedIndex::add_node(const std::string& node_name, const float* data, size_t n, std::vector<std::string>* touched,
+                          int level) {
+  if (n != dim_)  // core.rs:389-391
+    throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
+  // core.rs:393-409: the duplicate check is skipped for the first node of an empty index
+  if (!ids_.empty() && ids_.count(node_name))
+    throw HNSWError("Node: " + rust_debug_str(node_name) + " already exists", HNSW_ERR_EXISTS);
+  uint32_t id = 0;
+  check(hnsw_index_add(h_, data, n, level, &id));
+  if (id != names_.size()) throw HNSWError("device id out of sequence");
+  names_.push_back(node_name);
+  alive_.push_back(1);
+  ids_[node_name] = id;
+  if (touched) *touched = touched_names();  // core.rs:580-584
+}
+
+void NamedIndex::delete_node(const std::string& node_name, std::vector<std::string>* touched) {
+  auto it = ids_.find(node_name);
+  if (it == ids_.end())  // core.rs:419-422
+    throw HNSWError("Node: " + rust_debug_str(node_name) + " does not exist", HNSW_ERR_NOT_FOUND);
+  const uint32_t id = it->second;
+  check(hnsw_index_delete(h_, id));
+  ids_.erase(it);
+  alive_[id] = 0;
+  if (touched) *touched = touched_names();  // core.rs:443-447 (the victim itself is never reported)
+  names_[id].clear();
+}
+
+static std::string last_segment(const std::string& full) {  // core.rs:885-887
+  size_t p = full.rfind('.');
+  return p == std::string::npos ? full : full.substr(p + 1);
+}
+
+std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_t k, uint32_t ef) const {
+  if (n != dim_)  // core.rs:478-480
+    throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
+  std::vector<SearchResult> out;
+  if (k == 0) return out;
+  std::vector<uint32_t> ids(k);
+  std::vector<float> sims(k);
+  uint32_t cnt = 0;
+  check(hnsw_index_search(h_, q, n, (uint32_t)k, ef, ids.data(), sims.data(), &cnt));
+  out.reserve(cnt);
+  for (uint32_t i = 0; i < cnt; ++i) {
+    SearchResult r;
+    r.sim = sims[i];
+    r.name = last_segment(names_[ids[i]]);
+    r.data.resize(dim_);
+    check(hnsw_index_node_vector(h_, ids[i], r.data.data()));  // core.rs:888 copies the stored vector
+    out.push_back(std::move(r));
+  }
+  return out;
+}
+
+std::vector<std::vector<SearchResult>> NamedIndex::search_knn_batch(const float* q, size_t nq, size_t n, size_t k,
+                                                                     uint32_t ef, bool with_data) const {
+  if (n != dim_)
+    throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
+  std::vector<std::vector<SearchResult>> out(nq);
+  if (k == 0 || nq == 0) return out;
+  std::vector<uint32_t> ids(nq * k), counts(nq);
+  std::vector<float> sims(nq * k);
+  check(hnsw_index_search_batch(h_, nq, q, (uint32_t)k, ef, ids.data(), sims.data(), counts.data(), nullptr));
+  for (size_t i = 0; i < nq; ++i) {
+    out[i].reserve(counts[i]);
+    for (uint32_t j = 0; j < counts[i]; ++j) {
+      SearchResult r;
+      r.sim = sims[i * k + j];
+      r.name = last_segment(names_[ids[i * k + j]]);
+      if (with_data) {
+        r.data.resize(dim_);
+        check(hnsw_index_node_vector(h_, ids[i * k + j], r.data.data()));
+      }
+      out[i].push_back(std::move(r));
+    }
+  }
+  return out;
+}
+
+std::vector<std::string> NamedIndex::node_names() const {
+  std::vector<std::string> out;
+  out.reserve(ids_.size());
+  for (size_t i = 0; i < names_.size(); ++i)
+    if (alive_[i]) out.push_back(names_[i]);
+  return out;
+}
+
+// From<Index> for IndexRedis (types.rs:62-91)
+IndexRecord NamedIndex::to_record() const {
+  hnsw_params_t p = params();
+  IndexRecord r;
+  r.name = name_;
+  r.data_dim = p.data_dim;
+  r.m = p.m;
+  r.m_max = p.m_max;
+  r.m_max_0 = p.m_max_0;
+  r.ef_construction = p.ef_construction;
+  r.level_mult = p.level_mult;
+  r.node_count = p.node_count;
+  r.max_layer = (uint64_t)std::max(0, p.max_layer);
+  // `layers`: one set per level 0..max_layer; a node sits in the set of its own top level (core.rs:596).  An index
+  // that never held a node has no layer at all (core.rs:341).
+  if (!names_.empty() || p.node_count) r.layers.resize((size_t)r.max_layer + 1);
+  for (size_t i = 0; i < names_.size(); ++i) {
+    if (!alive_[i]) continue;
+    int32_t lv = 0;
+    check(hnsw_index_node_level(h_, (uint32_t)i, &lv));
+    if (lv < 0) continue;
+    if ((size_t)lv >= r.layers.size()) r.layers.resize((size_t)lv + 1);
+    r.layers[(size_t)lv].push_back(names_[i]);
+    r.nodes.push_back(names_[i]);
+  }
+  if (p.enterpoint != HNSW_NO_NODE) r.enterpoint = names_[p.enterpoint];
+  return r;
+}
+
+// From<&Node> for NodeRedis (types.rs:292-309)
+NodeRecord NamedIndex::node_record(const std::string& node_name) const {
+  auto it = ids_.find(node_name);
+  if (it == ids_.end()) throw HNSWError("Node: " + node_name + " does not exist", HNSW_ERR_NOT_FOUND);
+  const uint32_t id = it->second;
+  NodeRecord r;
+  r.data.resize(dim_);
+  check(hnsw_index_node_vector(h_, id, r.data.data()));
+  int32_t lv = 0;
+  check(hnsw_index_node_level(h_, id, &lv));
+  std::vector<uint32_t> buf(256);
+  for (int32_t l = 0; l <= lv; ++l) {
+    uint64_t n = 0;
+    check(hnsw_index_node_neighbors(h_, id, (uint32_t)l, buf.data(), buf.size(), &n));
+    if (n > buf.size()) {
+      buf.resize(n);
+      check(hnsw_index_node_neighbors(h_, id, (uint32_t)l, buf.data(), buf.size(), &n));
+    }
+    std::vector<std::string> layer;
+    layer.reserve(n);
+    for (uint64_t j = 0; j < n; ++j) layer.push_back(names_[buf[j]]);
+    r.neighbors.push_back(std::move(layer));
+  }
+  return r;
+}
+
+// make_index (lib.rs:252-315) in one pass: ids follow the order of ir.nodes; a node's level is the layer set that
+// lists it (lib.rs:289-300); its adjacency lists keep their stored order (lib.rs:275-286); the whole graph goes to the
+// device with one hnsw_index_load_graph call instead of per-node pointer fix-ups.
+void NamedIndex::restore_graph(const IndexRecord& ir, const std::vector<const NodeRecord*>& recs) {
+  const size_t n = ir.nodes.size();
+  names_ = ir.nodes;
+  alive_.assign(n, 1);
+  ids_.clear();
+  ids_.reserve(n * 2);
+  for (size_t i = 0; i < n; ++i) ids_[names_[i]] = (uint32_t)i;
+  if (ids_.size() != n) throw HNSWError("duplicate node name in the index record");
+  auto id_of = [&](const std::string& nn) -> uint32_t {
+    auto it = ids_.find(nn);
+    if (it == ids_.end()) throw HNSWError("Node: " + nn + " does not exist", HNSW_ERR_NOT_FOUND);  // lib.rs:281,295,308
+    return it->second;
+  };
+  std::vector<int32_t> levels(n, -2);
+  for (size_t l = 0; l < ir.layers.size(); ++l)
+    for (const std::string& nn : ir.layers[l]) levels[id_of(nn)] = (int32_t)l;
+  std::vector<float> vecs(n * (size_t)dim_);
+  std::vector<uint64_t> offs;
+  std::vector<uint32_t> nbrs;
+  offs.push_back(0);
+  for (size_t i = 0; i < n; ++i) {
+    const NodeRecord& r = *recs[i];
+    if (r.data.size() != dim_)
+      throw HNSWError("data dimension: " + std::to_string(r.data.size()) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
+    std::copy(r.data.begin(), r.data.end(), vecs.begin() + i * (size_t)dim_);
+    if (levels[i] == -2) levels[i] = r.neighbors.empty() ? 0 : (int32_t)r.neighbors.size() - 1;  // not listed in any layer
+    if ((int32_t)r.neighbors.size() > levels[i] + 1) levels[i] = (int32_t)r.neighbors.size() - 1;
+    for (int32_t l = 0; l <= levels[i]; ++l) {
+      if ((size_t)l < r.neighbors.size())
+        for (const std::string& nn : r.neighbors[(size_t)l]) nbrs.push_back(id_of(nn));
+      offs.push_back(nbrs.size());
+    }
+  }
+  int64_t entry = ir.enterpoint ? (int64_t)id_of(*ir.enterpoint) : -1;
+  if (nbrs.empty()) nbrs.push_back(0);
+  if (n == 0) return;
+  check(hnsw_index_load_graph(h_, n, vecs.data(), levels.data(), offs.data(), nbrs.data(), entry, (int32_t)ir.max_layer));
+}
+
+}  // namespace hnswhost
