@@ -91,7 +91,7 @@ def make_data(wl, nq_total):
     return x, q, levels
 
 
-def build_index(wl, x, levels, device, rank, world):
+def build_index(wl, x, levels, device, rank, world, options=()):
     """Rank 0 builds with the batched device builder; other ranks receive the device buffers over NCCL."""
     import torch
 
@@ -99,6 +99,9 @@ def build_index(wl, x, levels, device, rank, world):
 
     n, dim, m, efc, _, _ = WORKLOADS[wl]
     dev = r.DeviceIndex(dim, m, efc, device=device)
+    for opt in options:
+        name, val = opt.split("=")
+        dev.set_option(name, int(val))
     build_s = None
     if rank == 0:
         dev.reserve(n)
@@ -179,10 +182,7 @@ def main():
     x, q_all, levels = make_data(wl, nq * (world if args.impl != "reference" else 1))
     log("data ready in %.1f s" % (time.perf_counter() - t_setup))
     dev, build_s = build_index(wl, x, levels, local_rank, rank if args.impl != "reference" else 0,
-                               world if args.impl != "reference" else 1)
-    for opt in args.option:
-        name, val = opt.split("=")
-        dev.set_option(name, int(val))
+                               world if args.impl != "reference" else 1, args.option)
 
     # operating point: smallest ef with recall@10 >= 0.95 (rank 0 decides, everyone follows)
     ef, curve = args.ef, {}

@@ -182,7 +182,9 @@ int hnsw_index_adopt_replica(hnsw_index_t* idx);
 /* ---- tuning / diagnostics --------------------------------------------------------------------------- */
 
 /* Named integer options: "visited_slots" (per-query visited hash slots, power of two, 0 = auto),
- * "search_ctas_per_sm", "build_batch" (speculative insert batch size).  Unknown names -> HNSW_ERR_INVALID. */
+ * "search_ctas_per_sm", "build_batch" (nodes per batch of the FAST builder), "build_impl" (0 auto, 1 = register-staged
+ * batch searches, 2 = TMA-staged), "search_impl", "stage_rows", "recent_slots", "recent_tag", "block".
+ * Unknown names -> HNSW_ERR_INVALID. */
 int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t hnsw_launch_count(void);

@@ -1,7 +1,10 @@
 // Mutation entry points of the C ABI (insert / delete / replication).  Kernels: build.cuh.
 #define HNSW_PLAIN_BUILD_KERNELS
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/hnsw_b200.h"
@@ -123,7 +126,31 @@ struct FastPlan {
   size_t smem = 0;
 };
 
+// HNSW_BUILD_TRACE=1: per-phase wall time of every batch that takes longer than HNSW_BUILD_TRACE_MS (default 20)
+struct BatchTrace {
+  bool on;
+  double t0, last, ms[6] = {0, 0, 0, 0, 0, 0};
+  cudaStream_t s;
+  static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  explicit BatchTrace(cudaStream_t st) : on(std::getenv("HNSW_BUILD_TRACE") != nullptr), s(st) { t0 = last = on ? now() : 0; }
+  void mark(int phase) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    double t = now();
+    ms[phase] += t - last;
+    last = t;
+  }
+  void report(uint32_t first, uint32_t count) {
+    if (!on) return;
+    const char* lim = std::getenv("HNSW_BUILD_TRACE_MS");
+    if (now() - t0 < (lim ? std::atof(lim) : 20.0)) return;
+    std::fprintf(stderr, "[build] batch first=%u count=%u setup=%.1f K1=%.1f K2=%.1f K3=%.1f K4=%.1f finish=%.1f ms\n", first, count,
+                 ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
+  }
+};
+
 int Index::fast_batch(uint32_t first, uint32_t count) {
+  BatchTrace tr(stream);
   const int efr = build_efr(*this);
   const uint32_t W = g.W, lcap = list_capacity(W);
   // link tasks: (node, level) for level = 0 .. min(level(node), max_layer)
@@ -154,8 +181,7 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   const int grid1b = (int)std::min<uint64_t>((uint64_t)num_sms, (count + warps1b - 1) / warps1b);
   const size_t vis1 = vis_smem ? 0 : (size_t)grid1 * warps * slots * 4;
   const size_t vis1b = (size_t)grid1b * warps1b * big_slots * 4;
-  int rc = ensure_scratch(s_bvis, vis1 + vis1b);
-  if (rc) return rc;
+  int rc = HNSW_OK;
 
   // scratch layout
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -170,7 +196,14 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
                o_retry = take((size_t)count * 4), o_wn = take((size_t)wl_cap * 4), o_wlv = take((size_t)wl_cap * 4),
                o_wlen = take((size_t)wl_cap * 8), o_wold = take((size_t)wl_cap * lcap * 4),
                o_wnew = take((size_t)wl_cap * W * 4);
-  if ((rc = ensure_scratch(s_build, off))) return rc;
+  {
+    // Allocate once for the largest batch this add_batch call will reach (cudaMalloc / cudaFree of scratch that grows
+    // with every batch of the ramp cost 30-800 ms each on the test box: profiles/r1d_build.md), lay out for this one.
+    const size_t hc = std::max<size_t>(count, build_hint), ht = hc + hc / 2 + 64, hw = 6 * hc + 1024;
+    const size_t want = al((size_t)kCtlWords * 4) + 2 * al(hc * 4) + 3 * al(ht * 4) + al(ht * m * 4) + 2 * al(hw * 4) + al(hw * 8) +
+                        al(hw * (size_t)lcap * 4) + al(hw * (size_t)W * 4);
+    if ((rc = ensure_scratch(s_build, std::max(off, want)))) return rc;
+  }
   char* base = (char*)s_build.p;
   cudaError_t e = cudaMemsetAsync(base + o_ctl, 0, (size_t)kCtlWords * 4, stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(base + o_tb, task_base.data(), (size_t)count * 4, cudaMemcpyHostToDevice, stream);
@@ -207,17 +240,48 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   a.wl_old = (uint32_t*)(base + o_wold);
   a.wl_new = (uint32_t*)(base + o_wnew);
 
-  // K1 (+ retry pass with large global-memory visited tables)
-  LaunchCfg c1{grid1, block, smem1, stream};
-  e = run(kind, id1, efr, c1, g, &a);
-  if (e != cudaSuccess) return cuda_fail(e, "build_search launch");
-  FastArgs a1b = a;
-  a1b.retry_pass = 1;
-  a1b.vis_slots = big_slots;
-  a1b.vis_global = (uint32_t*)((char*)s_bvis.p + vis1);
-  LaunchCfg c1b{grid1b, block1b, (size_t)warps1b * qs, stream};
-  e = run(kind, kKernBuildSearchGlobal, efr, c1b, g, &a1b);
-  if (e != cudaSuccess) return cuda_fail(e, "build_search retry launch");
+  tr.mark(0);
+  // K1
+  bool staged = !kind_needs_smem_query(kind) && opt_build_impl != 1;
+  if (staged) {
+    // TMA-staged searches with a lossy visited table (build2.cuh): no retry pass, many more warps per SM
+    const int S = dim == 32 ? 32 : (dim <= 128 ? 8 : 4);  // BuildStage<C>::S
+    uint32_t vslots = next_pow2(std::max<uint64_t>(1024, (uint64_t)ef_construction * 16));
+    int vbits = 0;
+    while ((1u << vbits) < vslots) ++vbits;
+    const bool tag16 = vbits + 15 < 32 && n_ids <= (1ull << (vbits + 15));
+    const size_t per_warp = warp2_smem_bytes(dim, S, vslots, tag16 ? 2 : 4);
+    int blk = 64;
+    while (blk > 32 && (size_t)(blk / 32) * per_warp > max_smem) blk /= 2;
+    const int w2 = blk / 32;
+    const size_t smem2 = (size_t)w2 * per_warp;
+    const int id2 = kKernBuildSearch2 + (tag16 ? 1 : 0);
+    int occ2 = smem2 <= max_smem ? occupancy(kind, id2, efr, blk, smem2) : 0;
+    if (occ2 < 1) {
+      staged = false;
+    } else {
+      FastArgs a2 = a;
+      a2.vis_slots = vslots;
+      LaunchCfg c2{(int)std::min<uint64_t>((uint64_t)num_sms * occ2, (count + w2 - 1) / w2), blk, smem2, stream};
+      e = run(kind, id2, efr, c2, g, &a2);
+      if (e != cudaSuccess) return cuda_fail(e, "build_search2 launch");
+    }
+  }
+  if (!staged) {  // register-staged searches with an exact visited set (+ retry pass with large global-memory tables)
+    if ((rc = ensure_scratch(s_bvis, vis1 + vis1b))) return rc;
+    a.vis_global = (uint32_t*)s_bvis.p;
+    LaunchCfg c1{grid1, block, smem1, stream};
+    e = run(kind, id1, efr, c1, g, &a);
+    if (e != cudaSuccess) return cuda_fail(e, "build_search launch");
+    FastArgs a1b = a;
+    a1b.retry_pass = 1;
+    a1b.vis_slots = big_slots;
+    a1b.vis_global = (uint32_t*)((char*)s_bvis.p + vis1);
+    LaunchCfg c1b{grid1b, block1b, (size_t)warps1b * qs, stream};
+    e = run(kind, kKernBuildSearchGlobal, efr, c1b, g, &a1b);
+    if (e != cudaSuccess) return cuda_fail(e, "build_search retry launch");
+  }
+  tr.mark(1);
   // K2
   {
     const int blk = 256, w = blk / 32;
@@ -225,6 +289,7 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
     e = launch_plain(build_link_kernel, c, g, a);
     if (e != cudaSuccess) return cuda_fail(e, "build_link launch");
   }
+  tr.mark(2);
   // K3
   {
     const uint32_t cap = m_max_0;
@@ -243,6 +308,7 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
     e = run(kind, kKernBuildReprune, efr, c, g, &a3);
     if (e != cudaSuccess) return cuda_fail(e, "build_reprune launch");
   }
+  tr.mark(3);
   // K4
   {
     const int blk = 128, w = blk / 32;
@@ -255,11 +321,14 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   e = cudaMemcpyAsync(h, a.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) return cuda_fail(e, "build batch");
+  tr.mark(4);
   if ((rc = pull_meta())) return rc;
   build_stats[0] += count;
   build_stats[1] += h[kCtlWlDropped] + h[kCtlSkipped];
   build_stats[2] += h[kCtlReprunes];
   build_stats[3] += h[kCtlDistEvals];
+  tr.mark(5);
+  tr.report(first, count);
   if (device_error) {
     int err = device_error;
     device_error = 0;
@@ -273,7 +342,8 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
 }
 
 int Index::add_fast(uint32_t first, uint32_t count) {
-  const uint32_t bmax = opt_build_batch ? opt_build_batch : 4096;
+  const uint32_t bmax = opt_build_batch ? opt_build_batch : 8192;
+  build_hint = (uint32_t)std::min<uint64_t>(bmax, std::max<uint64_t>(1, (node_count + count) / 32));
   uint32_t pos = 0;
   int rc;
   while (pos < count) {

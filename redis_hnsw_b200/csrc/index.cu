@@ -641,6 +641,9 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
   } else if (n == "build_batch") {
     if (value < 1) return fail(HNSW_ERR_INVALID, "build_batch must be >= 1");
     ix.opt_build_batch = (uint32_t)value;
+  } else if (n == "build_impl") {
+    if (value < 0 || value > 2) return fail(HNSW_ERR_INVALID, "build_impl must be 0 (auto), 1 (register-staged) or 2 (TMA-staged)");
+    ix.opt_build_impl = (int)value;
   } else {
     return fail(HNSW_ERR_INVALID, "unknown option %s", name);
   }

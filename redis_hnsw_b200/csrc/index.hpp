@@ -56,6 +56,7 @@ struct Index {
   int opt_recent_tag = 0;         // 0 auto (16-bit tags when every id fits), 32 = force 32-bit entries
   uint32_t opt_recent_slots = 0;  // direct-mapped visited slots of the TMA-staged kernel, 0 = auto
   uint32_t opt_build_batch = 0;
+  int opt_build_impl = 0;         // 0 auto (TMA-staged K1 where a staged kernel exists), 1 = register-staged K1
   uint32_t auto_vis_ef = 0, auto_vis_slots = 0;  // adaptive visited-table size for the last-used ef
   uint32_t* h_retry_seen = nullptr;              // pinned: retry count of the previous async search
 
@@ -63,6 +64,7 @@ struct Index {
   uint32_t* d_stamp0 = nullptr;   // [cap_nodes] worklist de-duplication stamps (level-0 rows)
   uint32_t* d_stampU = nullptr;   // [cap_upper]
   uint32_t epoch = 0;
+  uint32_t build_hint = 0;        // largest batch the running add_batch call will reach (scratch is sized once)
   uint32_t exact_vis_slots = 0;
 
   // scratch

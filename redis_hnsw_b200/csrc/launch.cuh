@@ -3,6 +3,7 @@
 #include "build.cuh"
 #include "search.cuh"
 #include "search2.cuh"
+#include "build2.cuh"
 
 namespace hnsw {
 
@@ -38,6 +39,8 @@ enum KernelId : int {
   // search_knn2_kernel (TMA-staged rows): id = kKernSearch2 + 2 * log2(S / 4) + (16-bit visited tags ? 1 : 0)
   kKernSearch2 = 16,
 };
+// build_search2_kernel (TMA-staged K1 of the batched builder): id = kKernBuildSearch2 + (16-bit visited tags ? 1 : 0)
+constexpr int kKernBuildSearch2 = 32;
 inline int search2_id(int S, bool tag16) { return kKernSearch2 + 2 * (S == 4 ? 0 : S == 8 ? 1 : S == 16 ? 2 : 3) + (tag16 ? 1 : 0); }
 
 // kernel arguments are passed type-erased so that one entry point per kind serves every kernel
@@ -101,6 +104,8 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
       case kKernSearch2 + 5: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint16_t>), SearchArgs)
       case kKernSearch2 + 6: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint32_t>), SearchArgs)
       case kKernSearch2 + 7: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t>), SearchArgs)
+      case kKernBuildSearch2 + 0: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
+      case kKernBuildSearch2 + 1: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint16_t>), FastArgs)
     }
   }
 #undef HNSW_RUN

@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Secondary measurements on one GPU (not the headline bench): per-command latencies of the reference's three mutating /
+querying operators on a big index, GPU vs the CPU oracle on the SAME graph.
+
+  HNSW.SEARCH   one query per call (hnsw_index_search): the reference's command granularity (lib.rs:462-496)
+  HNSW.NODE.ADD one node per call (hnsw_index_add, EXACT) and as one EXACT stream (hnsw_index_add_batch)
+  HNSW.NODE.DEL one node per call (hnsw_index_delete)
+
+    python tools/bench_ops.py [--workload 1Mx128_M16_efc200] > gpurun_out/ops.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (workload table + data)
+
+
+def pct(a, p):
+    return float(np.percentile(np.asarray(a) * 1e6, p))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="1Mx128_M16_efc200")
+    ap.add_argument("--ef", type=int, default=64)
+    ap.add_argument("--n-search", type=int, default=2000)
+    ap.add_argument("--n-add", type=int, default=1000)
+    ap.add_argument("--n-del", type=int, default=300)
+    ap.add_argument("--cpu-add", type=int, default=200)
+    ap.add_argument("--cpu-del", type=int, default=100)
+    args = ap.parse_args()
+    import oracle
+    import redis_hnsw_b200 as r
+    from redis_hnsw_b200 import data
+
+    wl = args.workload
+    n, dim, m, efc, ds, rr = bench.WORKLOADS[wl]
+    extra_n = 2 * args.n_add + args.cpu_add
+    x, q_all, levels = bench.make_data(wl, args.n_search + extra_n)   # new points: same distribution as the data
+    q, extra = q_all[:args.n_search], q_all[args.n_search:]
+    lv_extra = data.draw_levels(extra_n, m, seed=4242)
+    dev = r.DeviceIndex(dim, m, efc)
+    dev.reserve(n + extra_n)
+    t0 = time.perf_counter()
+    dev.add_batch(x, levels, mode=r.BUILD_FAST)
+    build_s = time.perf_counter() - t0
+    out = {"workload": wl, "n": n, "dim": dim, "M": m, "ef_construction": efc, "ef_search": args.ef,
+           "fast_build_s": build_s}
+
+    orc = oracle.Oracle(dim, m, efc)
+    orc.import_graph(x, dev.export_graph())
+
+    # ---- HNSW.SEARCH, one query per call
+    for i in range(20):
+        dev.search(q[i], 10, ef=args.ef)
+    lat = []
+    for i in range(args.n_search):
+        t = time.perf_counter()
+        ids, sims = dev.search(q[i], 10, ef=args.ef)
+        lat.append(time.perf_counter() - t)
+    clat = []
+    for i in range(args.n_search):
+        t = time.perf_counter()
+        oids, osims = orc.search(q[i], 10, ef=args.ef)
+        clat.append(time.perf_counter() - t)
+    out["search_single"] = {"gpu_us_p50": pct(lat, 50), "gpu_us_p99": pct(lat, 99), "cpu_oracle_us_p50": pct(clat, 50),
+                            "cpu_oracle_us_p99": pct(clat, 99), "n": args.n_search,
+                            "note": "python ctypes call overhead (~5 us) included on both sides"}
+
+    # ---- HNSW.NODE.ADD: CPU oracle first (on its own copy of the graph), then the device, same vectors and levels
+    t = time.perf_counter()
+    for i in range(args.cpu_add):
+        orc.add(extra[i], int(lv_extra[i]))
+    cpu_add_s = (time.perf_counter() - t) / args.cpu_add
+    alat = []
+    for i in range(args.n_add):
+        t = time.perf_counter()
+        dev.add(extra[i], int(lv_extra[i]))
+        alat.append(time.perf_counter() - t)
+    st0 = dev.build_stats()
+    t = time.perf_counter()
+    dev.add_batch(extra[args.n_add:2 * args.n_add], lv_extra[args.n_add:2 * args.n_add], mode=r.BUILD_EXACT)
+    stream_s = (time.perf_counter() - t) / args.n_add
+    st1 = dev.build_stats()
+    out["node_add_exact"] = {"gpu_single_us_p50": pct(alat, 50), "gpu_single_us_p99": pct(alat, 99),
+                             "gpu_stream_us_per_insert": stream_s * 1e6, "gpu_stream_inserts_per_s": 1.0 / stream_s,
+                             "cpu_oracle_us_per_insert": cpu_add_s * 1e6, "cpu_oracle_inserts_per_s": 1.0 / cpu_add_s,
+                             "dist_evals_per_insert_stream": (st1["dist_evals"] - st0["dist_evals"]) / args.n_add,
+                             "n_gpu": args.n_add, "n_cpu": args.cpu_add}
+    # the first cpu_add inserts saw the same graph on both sides: their adjacency must agree
+    same = all(np.array_equal(dev.node_neighbors(n + i, 0), orc.node_neighbors(n + i, 0)) for i in range(0, args.cpu_add, 7))
+    out["node_add_exact"]["lists_equal_oracle_on_shared_prefix"] = bool(same)
+
+    # ---- HNSW.NODE.DEL
+    rng = np.random.default_rng(1)
+    victims = rng.permutation(n)[:args.n_del]
+    t = time.perf_counter()
+    for v in victims[:args.cpu_del]:
+        orc.delete(int(v))
+    cpu_del_s = (time.perf_counter() - t) / args.cpu_del
+    dlat = []
+    for v in victims:
+        t = time.perf_counter()
+        dev.delete(int(v))
+        dlat.append(time.perf_counter() - t)
+    out["node_del"] = {"gpu_us_p50": pct(dlat, 50), "gpu_us_p99": pct(dlat, 99), "cpu_oracle_us_per_delete": cpu_del_s * 1e6,
+                       "n_gpu": args.n_del, "n_cpu": args.cpu_del}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
