@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Small end-to-end run of every kernel family (metric, both search kernels, search_level, EXACT and FAST insert, delete)
+meant to be run under compute-sanitizer:  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import redis_hnsw_b200 as r
+from redis_hnsw_b200 import data
+
+for dim, m, efc in ((128, 16, 64), (32, 5, 40), (20, 6, 32), (96, 8, 32)):
+    n = 1500
+    x, q = data.uniform(n, dim, seed=1, n_queries=64)
+    lv = data.draw_levels(n, m, seed=2)
+    a = r.l2_batch(x[:256], x[256:512])
+    dev = r.DeviceIndex(dim, m, efc)
+    dev.add_batch(x[:600], lv[:600], mode=r.BUILD_EXACT)
+    dev.add_batch(x[600:], lv[600:], mode=r.BUILD_FAST)
+    for i in range(5):
+        dev.add(q[i], -1)
+    ids, sims, cnt, st = dev.search_batch(q, 10, ef=48, stats=True)
+    ids2, sims2, cnt2 = dev.search_batch(q, 10, ef=48)
+    assert np.array_equal(ids, ids2)
+    dev.search(q[0], 5)
+    dev.search_level(q[0], int(dev.params()["enterpoint"]), 8, 0)
+    for v in (3, 700, int(dev.params()["enterpoint"]), 1499):
+        dev.delete(v)
+    g = dev.export_graph()
+    dev.close()
+    print("ok", dim, m, efc, int(cnt.sum()), flush=True)
