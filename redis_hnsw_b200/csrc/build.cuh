@@ -801,6 +801,7 @@ __global__ void __launch_bounds__(256) build_apply_kernel(Graph g, FastArgs a) {
         for (uint32_t j = 0; j < n_new; ++j) {
           if (list_find(old, n_old, newl[j], lane) >= 0) continue;
           if (list_find(edit, len, newl[j], lane) >= 0 || len + 1 > a.lcap) continue;
+          __syncwarp();
           if (lane == 0) edit[len] = newl[j];
           ++len;
           __syncwarp();

@@ -77,3 +77,258 @@ __global__ void __launch_bounds__(256) build_search2_kernel(Graph g, FastArgs a)
 }
 
 }  // namespace hnsw
+
+// ================================================================ EXACT insert / delete on the staged machinery
+//
+// insert_exact_kernel / delete_exact_kernel (build.cuh) are one warp walking a chain of dependent hops; with the
+// register-staged distance provider a hop fetches its <= 32 new rows four at a time (five memory round trips per hop).
+// Here a hop stages all of them with one round of bulk-async copies (S = 32 rows for dim <= 128), and the re-selection
+// sweeps (core.rs:568, :853) run on the same stage.  The visited set is the lossy exact-tag table; candidate lists are
+// protected by the explicit membership test of eval_and_admit, so the selected sets are the reference's.
+namespace hnsw {
+
+template <int C>
+struct ExactStage {
+  static constexpr int S = (C <= 4) ? 32 : 8;
+};
+
+template <int C, int S, class T>
+__device__ __forceinline__ void load_q_from_slab(Warp2<C, S, T>& w, const Graph& g, uint32_t node, int lane) {
+  constexpr int V = RowRegs<C>::V;
+  const float* row = g.vecs + (size_t)node * (32 * C);
+#pragma unroll
+  for (int c = 0; c < C; ++c) w.q[c] = row[((c / V) * 32 + lane) * V + (c % V)];
+}
+
+// select_neighbors(e, N(e), cap, lc, ignored) as insert (core.rs:568) and delete (core.rs:853) call it; see
+// reprune_select in build.cuh.  w.q holds e's vector.
+template <int EFR, int C, int S, class T>
+__device__ __forceinline__ void reprune_select2(const Graph& g, Warp2<C, S, T>& w, uint32_t e, uint32_t level, int cap,
+                                                const uint32_t* old, uint32_t n_old, CandList<EFR>& L, Counters& cnt,
+                                                int lane, uint32_t ignored) {
+  w.seen.clear(lane);
+  L.init();
+  auto feed = [&](uint32_t nb) {
+    if (nb == e || nb == ignored) nb = kEmpty;                   // never candidates (core.rs:704-708, 728-731)
+    expand_chunk2<EFR, C, S, T>(g, w, nb, cap, L, cnt, nullptr, lane);
+  };
+  for (uint32_t i = 0; i < n_old; i += 32) feed((i + lane < n_old) ? old[i + lane] : kEmpty);   // core.rs:549-557
+  for (uint32_t j = 0; j < n_old; ++j) {                         // extend_candidates (core.rs:698-721)
+    uint32_t* ovf;
+    const uint32_t* row = row_ptr(g, old[j], level, &ovf);
+    if (!row) continue;
+    uint32_t link = *ovf;
+    bool more = true;
+    for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
+      const uint32_t nb = row[c * 32 + lane];
+      more = __shfl_sync(kFull, nb, 31) != kEmpty;
+      feed(nb);
+    }
+    while (more && link != kEmpty) {
+      uint32_t nb = g.pool[(size_t)link * 32 + lane];
+      link = __shfl_sync(kFull, nb, 31);
+      if (lane == 31) nb = kEmpty;
+      feed(nb);
+    }
+  }
+}
+
+template <int C, int S, class T>
+__device__ __forceinline__ unsigned char* warp2_setup(Warp2<C, S, T>& w, unsigned char* base, uint32_t vis_slots, int lane) {
+  w.stage = reinterpret_cast<const float4*>(base);
+  w.stage_s = smem_u32(base);
+  const uint32_t tab_bytes = (vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
+  w.seen.tab = reinterpret_cast<T*>(base + (size_t)S * C * 128);
+  w.seen.n16 = tab_bytes / 16;
+  w.seen.bits = 31 - __clz(vis_slots);
+  w.ids = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128 + tab_bytes);
+  w.bar = smem_u32(w.ids + 32);
+  w.parity = 0;
+  if (lane == 0) mbar_init(w.bar, 1);
+  __syncwarp();
+  return base + warp2_smem_bytes(32 * C, S, vis_slots, sizeof(T));
+}
+
+// update_node_connections (core.rs:776-822) for node `e` whose re-selected list is in L; shared by insert and delete.
+template <int EFR, class Touch>
+__device__ __forceinline__ void apply_reselection(const Graph& g, const CandList<EFR>& L, uint32_t e, uint32_t lc, uint32_t* erow,
+                                                  uint32_t* eovf, const uint32_t* old, uint32_t n_old, uint32_t* keep_add,
+                                                  uint32_t* rem, uint32_t* edit, uint32_t lcap, uint32_t victim, Touch touch,
+                                                  int lane) {
+  uint32_t n_keep, n_add, n_rem;
+  reprune_delta<EFR>(L, old, n_old, keep_add, rem, n_keep, n_add, n_rem, lane);
+  list_store(g, erow, eovf, keep_add, n_keep + n_add, lane);
+  touch(e);
+  for (uint32_t t = 0; t < n_add; ++t) {                          // :793-796 (no cap check on the other side)
+    row_append_unique(g, keep_add[n_keep + t], lc, e, edit, lcap, lane);
+    touch(keep_add[n_keep + t]);
+  }
+  for (uint32_t t = 0; t < n_keep; ++t) touch(keep_add[t]);
+  for (uint32_t t = 0; t < n_rem; ++t) {                          // :805-816
+    if (rem[t] == victim) continue;                               // delete: not mirrored, not reported (core.rs:810-813)
+    row_remove(g, rem[t], lc, e, edit, lcap, lane);
+    touch(rem[t]);
+  }
+}
+
+// core.rs:383-412 + 489-599, one warp, the NODE.ADD stream in order (see insert_exact_kernel)
+template <int EFR, int C>
+__global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a) {
+  constexpr int S = ExactStage<C>::S;
+  using T = uint32_t;
+  extern __shared__ __align__(128) unsigned char smem2[];
+  const int lane = lane_id();
+  Warp2<C, S, T> w;
+  uint32_t* lists = reinterpret_cast<uint32_t*>(warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane));
+  // sel[m] | old[lcap] | keep_add[lcap + W] | rem[lcap] | edit[lcap]
+  uint32_t* sel = lists;
+  uint32_t* old = sel + ((a.m + 31) & ~31u);
+  uint32_t* keep_add = old + a.lcap;
+  uint32_t* rem = keep_add + a.lcap + g.W;
+  uint32_t* edit = rem + a.lcap;
+
+  CandList<EFR> L;
+  Counters cnt = {0, 0, 0};
+  uint32_t n_touched = 0, n_reprunes = 0;
+  auto touch = [&](uint32_t id) {
+    if (a.touched) {
+      if (lane == 0 && n_touched < a.touched_cap) a.touched[n_touched] = id;
+      ++n_touched;
+    }
+  };
+
+  for (uint32_t it = 0; it < a.count; ++it) {
+    const uint32_t q = a.first + it;
+    const int l = g.level[q];
+    const int l_max = g.meta[kMetaMaxLayer];                      // core.rs:496
+    uint32_t ep = (uint32_t)g.meta[kMetaEntry];                   // core.rs:508
+    for (int lc = l_max; lc >= 0; --lc) {
+      const bool link = lc <= l;
+      const uint32_t cap = lc == 0 ? a.cap0 : a.capU;             // core.rs:560
+      load_q_from_slab<C, S, T>(w, g, q, lane);
+      search_layer2<EFR, C, S, T>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane);   // :513, :524
+      float s;
+      L.get(0, lane, false, ep, s);                               // :514 / :576
+      if (!link) continue;
+      const uint32_t n_sel = min((uint32_t)L.len, a.m);           // core.rs:531 (build.cuh header)
+#pragma unroll
+      for (int r = 0; r < EFR; ++r) {
+        uint32_t e = r * 32 + lane;
+        if (e < n_sel) sel[e] = L.id[r] & ~kExpanded;
+      }
+      __syncwarp();
+      {                                                           // connect_neighbors (core.rs:759-774)
+        uint32_t* ovf;
+        uint32_t* row = row_ptr(g, q, (uint32_t)lc, &ovf);
+        list_store(g, row, ovf, sel, n_sel, lane);
+      }
+      for (uint32_t i = 0; i < n_sel; ++i) {
+        row_append_unique(g, sel[i], (uint32_t)lc, q, edit, a.lcap, lane);
+        touch(sel[i]);                                            // core.rs:535-537
+      }
+      for (uint32_t i = 0; i < n_sel; ++i) {                      // shrink connections (core.rs:540-574), nearest-first
+        const uint32_t e = sel[i];
+        uint32_t* eovf;
+        uint32_t* erow = row_ptr(g, e, (uint32_t)lc, &eovf);
+        const uint32_t n_old = list_load(g, erow, eovf, old, a.lcap, lane);
+        if (n_old == kEmpty) {
+          if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
+          continue;
+        }
+        if (n_old <= cap) continue;                               // core.rs:561
+        load_q_from_slab<C, S, T>(w, g, e, lane);
+        reprune_select2<EFR, C, S, T>(g, w, e, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, kEmpty);   // :568
+        ++n_reprunes;
+        apply_reselection<EFR>(g, L, e, (uint32_t)lc, erow, eovf, old, n_old, keep_add, rem, edit, a.lcap, kEmpty, touch, lane);
+      }
+    }
+    if (l > l_max && lane == 0) {                                 // core.rs:587-593
+      g.meta[kMetaMaxLayer] = l;
+      g.meta[kMetaEntry] = (int32_t)q;
+    }
+    __syncwarp();
+    if (lane == 0) a.ctl[kCtlProgress] = it + 1;
+  }
+  if (lane == 0) {
+    a.ctl[kCtlDistEvals] += cnt.n_dist;
+    a.ctl[kCtlReprunes] += n_reprunes;
+    a.ctl[kCtlTouched] = n_touched;
+  }
+}
+
+// core.rs:414-475 + 824-863 (see delete_exact_kernel)
+template <int EFR, int C>
+__global__ void __launch_bounds__(32) delete_exact2_kernel(Graph g, ExactArgs a) {
+  constexpr int S = ExactStage<C>::S;
+  using T = uint32_t;
+  extern __shared__ __align__(128) unsigned char smem2[];
+  const int lane = lane_id();
+  Warp2<C, S, T> w;
+  uint32_t* lists = reinterpret_cast<uint32_t*>(warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane));
+  // vlist[lcap] | old[lcap] | keep_add[lcap + W] | rem[lcap] | edit[lcap]
+  uint32_t* vlist = lists;
+  uint32_t* old = vlist + a.lcap;
+  uint32_t* keep_add = old + a.lcap;
+  uint32_t* rem = keep_add + a.lcap + g.W;
+  uint32_t* edit = rem + a.lcap;
+
+  CandList<EFR> L;
+  Counters cnt = {0, 0, 0};
+  uint32_t n_touched = 0, n_reprunes = 0;
+  auto touch = [&](uint32_t id) {
+    if (a.touched) {
+      if (lane == 0 && n_touched < a.touched_cap) a.touched[n_touched] = id;
+      ++n_touched;
+    }
+  };
+  const uint32_t victim = a.first;
+  const int top = g.level[victim];
+  bool ok = true;
+  for (int lc = 0; lc <= top && ok; ++lc) {                       // core.rs:434-440
+    const uint32_t cap = lc == 0 ? a.cap0 : a.capU;               // core.rs:846
+    uint32_t* vovf;
+    uint32_t* vrow = row_ptr(g, victim, (uint32_t)lc, &vovf);
+    if (!vrow) continue;
+    const uint32_t n_v = list_load(g, vrow, vovf, vlist, a.lcap, lane);
+    if (n_v == kEmpty) {
+      ok = false;
+      break;
+    }
+    for (uint32_t i = 0; i < n_v && ok; ++i) {                    // core.rs:829 list order
+      const uint32_t n = vlist[i];
+      uint32_t* novf;
+      uint32_t* nrow = row_ptr(g, n, (uint32_t)lc, &novf);
+      if (!nrow) continue;
+      const uint32_t n_old = list_load(g, nrow, novf, old, a.lcap, lane);   // nconn (core.rs:834-844)
+      if (n_old == kEmpty) {
+        ok = false;
+        break;
+      }
+      load_q_from_slab<C, S, T>(w, g, n, lane);
+      reprune_select2<EFR, C, S, T>(g, w, n, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, victim);   // :853
+      ++n_reprunes;
+      apply_reselection<EFR>(g, L, n, (uint32_t)lc, nrow, novf, old, n_old, keep_add, rem, edit, a.lcap, victim, touch, lane);  // :856
+    }
+  }
+  if (ok) {
+    for (int lc = 0; lc <= top; ++lc) {                           // the node is dropped (core.rs:419)
+      uint32_t* vovf;
+      uint32_t* vrow = row_ptr(g, victim, (uint32_t)lc, &vovf);
+      if (vrow) list_store(g, vrow, vovf, vlist, 0, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      g.level[victim] = -1;
+      a.ctl[kCtlProgress] = 1;
+    }
+  } else if (lane == 0) {
+    atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
+  }
+  if (lane == 0) {
+    a.ctl[kCtlDistEvals] += cnt.n_dist;
+    a.ctl[kCtlReprunes] += n_reprunes;
+    a.ctl[kCtlTouched] = n_touched;
+  }
+}
+
+}  // namespace hnsw

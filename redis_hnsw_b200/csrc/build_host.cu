@@ -57,6 +57,20 @@ static int build_efr(const Index& ix) { return std::max(efr_for(ix.ef_constructi
 
 // ---------------------------------------------------------------- EXACT
 
+// The one-warp EXACT kernels have a TMA-staged flavour (build2.cuh) for the dimensions with a staged search kernel:
+// stage of ExactStage<C>::S rows + 8192 32-bit visited tags + the list buffers.  Returns true (and the launch's shared
+// memory size / visited slots) when it applies.
+bool Index::exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) const {
+  if (kind_needs_smem_query(kind) || opt_build_impl == 1) return false;
+  const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
+  const uint32_t slots = 8192;
+  const size_t need = warp2_smem_bytes(dim, S, slots, 4) + list_bytes;
+  if (need > max_smem) return false;
+  *smem = need;
+  *vis_slots = slots;
+  return true;
+}
+
 int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
   if (count == 0) return HNSW_OK;
   const int efr = build_efr(*this);
@@ -84,8 +98,10 @@ int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
   a.touched = want_touched ? ctl + kCtlWords : nullptr;
   a.touched_cap = touched_cap;
   size_t smem = ((size_t)((m + 31) & ~31u) + 4 * (size_t)lcap + g.W) * 4 + (kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0);
+  int kern = kKernExact;
+  if (exact_staged(&smem, ((size_t)((m + 31) & ~31u) + 4 * (size_t)lcap + g.W) * 4, &a.vis_slots)) kern = kKernExact2;
   LaunchCfg c{1, 32, smem, stream};
-  e = run(kind, kKernExact, efr, c, g, &a);
+  e = run(kind, kern, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "insert_exact launch");
   uint32_t h[kCtlWords];
   e = cudaMemcpyAsync(h, ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
@@ -403,8 +419,10 @@ int Index::delete_node(uint32_t id) {
   a.touched = ctl + kCtlWords;
   a.touched_cap = touched_cap;
   size_t smem = (5 * (size_t)lcap + g.W) * 4 + (kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0);
+  int kern = kKernDelete;
+  if (exact_staged(&smem, (5 * (size_t)lcap + g.W) * 4, &a.vis_slots)) kern = kKernDelete2;
   LaunchCfg c{1, 32, smem, stream};
-  e = run(kind, kKernDelete, efr, c, g, &a);
+  e = run(kind, kern, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "delete_exact launch");
   uint32_t h[kCtlWords];
   e = cudaMemcpyAsync(h, ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);

@@ -100,6 +100,7 @@ struct Index {
   int add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id, bool want_touched);
   int add_exact(uint32_t first, uint32_t count, bool want_touched);
   int delete_node(uint32_t id);
+  bool exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) const;
   int add_fast(uint32_t first, uint32_t count);
   int fast_batch(uint32_t first, uint32_t count);
   int set_entry(int32_t entry, int32_t max_layer);

@@ -105,6 +105,7 @@ struct Recent {
   uint32_t n16;   // table bytes / 16
   int bits;       // B = log2(slots)
   __device__ __forceinline__ void clear(int lane) {
+    __syncwarp();  // every lane's test_and_set stores of the previous search are ordered before the wipe
     const uint32_t fill = sizeof(T) == 4 ? kEmpty : 0u;
     uint4 e = make_uint4(fill, fill, fill, fill);
     uint4* t = reinterpret_cast<uint4*>(tab);
