@@ -100,17 +100,49 @@ __device__ __forceinline__ void load_q_from_slab(Warp2<C, S, T>& w, const Graph&
   for (int c = 0; c < C; ++c) w.q[c] = row[((c / V) * 32 + lane) * V + (c % V)];
 }
 
+// address of the first 128-byte line of the adjacency row of (node, level) for an L2 prefetch, or null
+__device__ __forceinline__ const void* row_line(const Graph& g, uint32_t node, uint32_t level) {
+  if (level == 0) return g.adj0 + (size_t)node * g.W;
+  const uint32_t base = g.upper_base[node];
+  if (base == kEmpty || (int32_t)level > g.level[node]) return nullptr;
+  return g.adjU + (size_t)(base + level - 1) * g.W;
+}
+
 // select_neighbors(e, N(e), cap, lc, ignored) as insert (core.rs:568) and delete (core.rs:853) call it; see
-// reprune_select in build.cuh.  w.q holds e's vector.
+// reprune_select in build.cuh.  w.q holds e's vector.  The sweep is a SET computation (top-cap by sim of everything
+// reachable in two hops), so unseen ids are collected across adjacency rows in `pend` (shared memory, >= 64 words) and
+// evaluated 32 at a time: one staging round per 32 candidates instead of one per row walked.
 template <int EFR, int C, int S, class T>
 __device__ __forceinline__ void reprune_select2(const Graph& g, Warp2<C, S, T>& w, uint32_t e, uint32_t level, int cap,
                                                 const uint32_t* old, uint32_t n_old, CandList<EFR>& L, Counters& cnt,
-                                                int lane, uint32_t ignored) {
+                                                int lane, uint32_t ignored, uint32_t* pend) {
   w.seen.clear(lane);
   L.init();
+  for (uint32_t i = 0; i < n_old; i += 32)                       // the rows the sweep is about to walk
+    if (i + lane < n_old) {
+      const void* p = row_line(g, old[i + lane], level);
+      if (p) prefetch_l2(p);
+    }
+  uint32_t np = 0;                                                // warp-uniform number of pending ids
+  auto flush = [&](uint32_t n) {                                  // evaluate pend[0..n), n <= 32
+    __syncwarp();
+    const uint32_t nb = lane < (int)n ? pend[lane] : kEmpty;
+    const uint32_t rest = lane + 32 < (int)np ? pend[lane + 32] : kEmpty;
+    __syncwarp();
+    cnt.n_dist += n;
+    eval_and_admit<EFR, C, S, T>(g, w, nb, n >= 32 ? kFull : ((1u << n) - 1u), cap, L, nullptr, lane);
+    if (lane + 32 < (int)np) pend[lane] = rest;
+    np -= n;
+    __syncwarp();
+  };
   auto feed = [&](uint32_t nb) {
-    if (nb == e || nb == ignored) nb = kEmpty;                   // never candidates (core.rs:704-708, 728-731)
-    expand_chunk2<EFR, C, S, T>(g, w, nb, cap, L, cnt, nullptr, lane);
+    const bool valid = nb != kEmpty && nb != e && nb != ignored;  // never candidates (core.rs:704-708, 728-731)
+    const bool is_new = valid && w.seen.test_and_set(nb);
+    const uint32_t mask = __ballot_sync(kFull, is_new);
+    if (!mask) return;
+    if (is_new) pend[np + __popc(mask & ((1u << lane) - 1u))] = nb;
+    np += __popc(mask);
+    if (np >= 32) flush(32);
   };
   for (uint32_t i = 0; i < n_old; i += 32) feed((i + lane < n_old) ? old[i + lane] : kEmpty);   // core.rs:549-557
   for (uint32_t j = 0; j < n_old; ++j) {                         // extend_candidates (core.rs:698-721)
@@ -131,6 +163,7 @@ __device__ __forceinline__ void reprune_select2(const Graph& g, Warp2<C, S, T>& 
       feed(nb);
     }
   }
+  if (np) flush(np);
 }
 
 template <int C, int S, class T>
@@ -157,6 +190,10 @@ __device__ __forceinline__ void apply_reselection(const Graph& g, const CandList
                                                   int lane) {
   uint32_t n_keep, n_add, n_rem;
   reprune_delta<EFR>(L, old, n_old, keep_add, rem, n_keep, n_add, n_rem, lane);
+  for (uint32_t t = lane; t < n_add + n_rem; t += 32) {           // the rows the mirrored edits below will touch
+    const void* p = row_line(g, t < n_add ? keep_add[n_keep + t] : rem[t - n_add], lc);
+    if (p) prefetch_l2(p);
+  }
   list_store(g, erow, eovf, keep_add, n_keep + n_add, lane);
   touch(e);
   for (uint32_t t = 0; t < n_add; ++t) {                          // :793-796 (no cap check on the other side)
@@ -237,7 +274,7 @@ __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a)
         }
         if (n_old <= cap) continue;                               // core.rs:561
         load_q_from_slab<C, S, T>(w, g, e, lane);
-        reprune_select2<EFR, C, S, T>(g, w, e, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, kEmpty);   // :568
+        reprune_select2<EFR, C, S, T>(g, w, e, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, kEmpty, keep_add);   // :568
         ++n_reprunes;
         apply_reselection<EFR>(g, L, e, (uint32_t)lc, erow, eovf, old, n_old, keep_add, rem, edit, a.lcap, kEmpty, touch, lane);
       }
@@ -305,7 +342,7 @@ __global__ void __launch_bounds__(32) delete_exact2_kernel(Graph g, ExactArgs a)
         break;
       }
       load_q_from_slab<C, S, T>(w, g, n, lane);
-      reprune_select2<EFR, C, S, T>(g, w, n, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, victim);   // :853
+      reprune_select2<EFR, C, S, T>(g, w, n, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, victim, keep_add);   // :853
       ++n_reprunes;
       apply_reselection<EFR>(g, L, n, (uint32_t)lc, nrow, novf, old, n_old, keep_add, rem, edit, a.lcap, victim, touch, lane);  // :856
     }
