@@ -83,6 +83,7 @@ void NamedIndex::add_node(const std::string& node_name, const float* data, size_
   names_.push_back(node_name);
   alive_.push_back(1);
   ids_[node_name] = id;
+  ++epoch_;
   if (touched) *touched = touched_names();  // core.rs:580-584
 }
 
@@ -94,6 +95,7 @@ void NamedIndex::delete_node(const std::string& node_name, std::vector<std::stri
   check(hnsw_index_delete(h_, id));
   ids_.erase(it);
   alive_[id] = 0;
+  ++epoch_;
   if (touched) *touched = touched_names();  // core.rs:443-447 (the victim itself is never reported)
   names_[id].clear();
 }
@@ -212,6 +214,37 @@ NodeRecord NamedIndex::node_record(const std::string& node_name) const {
   return r;
 }
 
+NamedIndex::Snapshot NamedIndex::snapshot() const {
+  Snapshot s;
+  s.index = to_record();
+  uint64_t n_ids = 0, n_rows = 0, n_edges = 0;
+  check(hnsw_index_graph_sizes(h_, &n_ids, &n_rows, &n_edges));
+  if (n_ids == 0) return s;
+  std::vector<int32_t> levels(n_ids);
+  std::vector<uint64_t> offs(n_rows + 1);
+  std::vector<uint32_t> nbrs(std::max<uint64_t>(n_edges, 1));
+  int64_t entry = -1;
+  int32_t max_layer = 0;
+  check(hnsw_index_export_graph(h_, levels.data(), offs.data(), nbrs.data(), &entry, &max_layer));
+  std::vector<float> vecs(n_ids * (size_t)dim_);
+  check(hnsw_index_export_vectors(h_, vecs.data()));
+  s.nodes.reserve(ids_.size());
+  uint64_t row = 0;
+  for (uint64_t i = 0; i < n_ids; ++i) {
+    if (levels[i] < 0) continue;  // deleted: no rows
+    NodeRecord r;
+    r.data.assign(vecs.begin() + i * (size_t)dim_, vecs.begin() + (i + 1) * (size_t)dim_);
+    for (int32_t l = 0; l <= levels[i]; ++l, ++row) {
+      std::vector<std::string> layer;
+      layer.reserve(offs[row + 1] - offs[row]);
+      for (uint64_t e = offs[row]; e < offs[row + 1]; ++e) layer.push_back(names_[nbrs[e]]);
+      r.neighbors.push_back(std::move(layer));
+    }
+    s.nodes.emplace_back(names_[i], std::move(r));
+  }
+  return s;
+}
+
 // make_index (lib.rs:252-315) in one pass: ids follow the order of ir.nodes; a node's level is the layer set that
 // lists it (lib.rs:289-300); its adjacency lists keep their stored order (lib.rs:275-286); the whole graph goes to the
 // device with one hnsw_index_load_graph call instead of per-node pointer fix-ups.
@@ -249,6 +282,7 @@ void NamedIndex::restore_graph(const IndexRecord& ir, const std::vector<const No
     }
   }
   int64_t entry = ir.enterpoint ? (int64_t)id_of(*ir.enterpoint) : -1;
+  ++epoch_;
   if (nbrs.empty()) nbrs.push_back(0);
   if (n == 0) return;
   check(hnsw_index_load_graph(h_, n, vecs.data(), levels.data(), offs.data(), nbrs.data(), entry, (int32_t)ir.max_layer));

@@ -81,6 +81,15 @@ class NamedIndex {
   IndexRecord to_record() const;
   NodeRecord node_record(const std::string& node_name) const;
   std::vector<std::string> node_names() const;
+  // Every record at once, from two bulk device-to-host copies (graph + vector slab) instead of per-node getters:
+  // what a persistence snapshot needs (types.rs:243-284, 410-428 for the whole keyspace of one index).
+  struct Snapshot {
+    IndexRecord index;
+    std::vector<std::pair<std::string, NodeRecord>> nodes;
+  };
+  Snapshot snapshot() const;
+  // bumped by every mutation (add_node / delete_node / restore)
+  uint64_t epoch() const { return epoch_; }
 
   hnsw_index_t* handle() const { return h_; }
 
@@ -95,6 +104,7 @@ class NamedIndex {
   std::unordered_map<std::string, uint32_t> ids_;  // live names -> id
   std::vector<std::string> names_;                 // id -> name ("" once deleted)
   std::vector<char> alive_;
+  uint64_t epoch_ = 1;
 };
 
 template <class Fetch>

@@ -56,6 +56,16 @@ typedef struct RedisModuleTypeMethods {
   RedisModuleTypeFreeFunc free;
 } RedisModuleTypeMethods;
 
+/* Server events (Redis >= 6.0).  Optional: resolved if the host provides it (see RedisModule_Init below). */
+typedef struct RedisModuleEvent {
+  uint64_t id;
+  uint64_t dataver;
+} RedisModuleEvent;
+typedef void (*RedisModuleEventCallback)(RedisModuleCtx* ctx, RedisModuleEvent eid, uint64_t subevent, void* data);
+#define REDISMODULE_EVENT_PERSISTENCE 1
+/* subevents 0..2 (3 on Redis >= 7.0) announce that a snapshot is about to START: RDB, AOF rewrite, sync RDB, sync AOF */
+#define HNSW_PERSISTENCE_START_MAX_SUBEVENT 3
+
 #define HNSW_RM_API(X)                                                                                              \
   X(void*, Alloc, (size_t bytes))                                                                                   \
   X(void, Free, (void* ptr))                                                                                        \
@@ -101,6 +111,11 @@ typedef struct RedisModuleTypeMethods {
 #endif
 HNSW_RM_API(HNSW_RM_DECL)
 #undef HNSW_RM_DECL
+#ifdef HNSW_REDISMODULE_MAIN
+int (*RedisModule_SubscribeToServerEvent)(RedisModuleCtx* ctx, RedisModuleEvent event, RedisModuleEventCallback callback) = 0;
+#else
+extern int (*RedisModule_SubscribeToServerEvent)(RedisModuleCtx* ctx, RedisModuleEvent event, RedisModuleEventCallback callback);
+#endif
 
 #ifdef HNSW_REDISMODULE_MAIN
 /* What redismodule.h's RedisModule_Init does: the first word of the context is the GetApi resolver. */
@@ -112,6 +127,8 @@ static int RedisModule_Init(RedisModuleCtx* ctx, const char* name, int ver, int 
   if (get_api("RedisModule_" #fname, (void*)&RedisModule_##fname) != REDISMODULE_OK || !RedisModule_##fname) return REDISMODULE_ERR;
   HNSW_RM_API(HNSW_RM_GET)
 #undef HNSW_RM_GET
+  if (get_api("RedisModule_SubscribeToServerEvent", (void*)&RedisModule_SubscribeToServerEvent) != REDISMODULE_OK)
+    RedisModule_SubscribeToServerEvent = 0; /* optional */
   if (RedisModule_IsModuleNameBusy(name)) return REDISMODULE_ERR;
   RedisModule_SetModuleAttribs(ctx, name, ver, apiver);
   return REDISMODULE_OK;

@@ -8,7 +8,10 @@
 //     fake_redis_host <module.so> < script
 //
 // Each script line is one command (whitespace-separated words).  Meta commands:
-//     #SAVE <file>     rdb_save every module-typed key into <file>
+//     #SAVE <file>     rdb_save every module-typed key into <file> (in this process, like the SAVE command)
+//     #BGSAVE <file>   like BGSAVE: fire the persistence server event (RDB_START) in the parent, fork(), rdb_save every
+//                      key in the CHILD (which must not touch the parent's CUDA context), wait, fire the end event.
+//                      Set FAKE_REDIS_NO_EVENTS=1 to emulate a host without RedisModule_SubscribeToServerEvent.
 //     #LOAD <file>     rdb_load the keys of <file> into the (empty) keyspace
 //     #KEYS            reply: sorted [key, type-name] pairs
 //     #INFO            reply: module name/version, registered commands (name, flags, key spec) and data types
@@ -17,6 +20,8 @@
 // "inf" or "nan" marker ({"double": "..."} for non-finite), bulk strings as JSON strings, simple strings as
 // {"status": ...}, errors as {"error": ...}, null as null, arrays as arrays.
 #include <dlfcn.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -62,7 +67,13 @@ struct Command {
   int first, last, step;
 };
 
+struct ServerEvent {
+  uint64_t id, dataver;
+};
+typedef void (*EventCallback)(void* ctx, ServerEvent eid, uint64_t subevent, void* data);
+
 struct Host {
+  std::vector<std::pair<uint64_t, EventCallback>> subscribers;
   std::string module_name;
   int module_ver = 0, api_ver = 0;
   std::map<std::string, Command> commands;
@@ -319,7 +330,17 @@ static char* api_LoadStringBuffer(IO* io, size_t* lenptr) {
   return out;
 }
 
+static int api_SubscribeToServerEvent(void*, ServerEvent ev, EventCallback cb) {
+  H.subscribers.emplace_back(ev.id, cb);
+  return 0;
+}
+
 static int get_api(const char* name, void* target) {
+  if (std::string(name) == "RedisModule_SubscribeToServerEvent") {
+    if (std::getenv("FAKE_REDIS_NO_EVENTS")) return 1;
+    *(void**)target = (void*)api_SubscribeToServerEvent;
+    return 0;
+  }
   static const std::map<std::string, void*> table = {
 #define E(n) {"RedisModule_" #n, (void*)api_##n}
       E(Alloc), E(Free), E(CreateCommand), E(SetModuleAttribs), E(IsModuleNameBusy), E(WrongArity), E(AutoMemory),
@@ -408,26 +429,55 @@ static bool take_s(const std::string& b, size_t& pos, std::string* s) {
   return true;
 }
 
+static long long save_all(const std::string& path) {
+  std::string out;
+  uint64_t n = 0;
+  for (auto& kv : H.keys) n += kv.second.type != nullptr;
+  put_u64(out, n);
+  for (auto& kv : H.keys) {
+    if (!kv.second.type) continue;
+    IO io;
+    kv.second.type->m.rdb_save(&io, kv.second.value);
+    put_s(out, kv.first);
+    put_s(out, kv.second.type->name);
+    put_u64(out, (uint64_t)kv.second.type->encver);
+    put_s(out, io.buf);
+  }
+  std::ofstream f(path, std::ios::binary);
+  f.write(out.data(), (std::streamsize)out.size());
+  return f.good() ? (long long)n : -1;
+}
+
+static void fire_event(uint64_t id, uint64_t subevent) {
+  Ctx c{};
+  c.get_api = (void*)get_api;
+  for (auto& sub : H.subscribers)
+    if (sub.first == id) sub.second(&c, ServerEvent{id, 1}, subevent, nullptr);
+}
+
 static Reply meta(const std::vector<std::string>& w) {
   Reply r;
   if (w[0] == "#SAVE" && w.size() == 2) {
-    std::string out;
-    uint64_t n = 0;
-    for (auto& kv : H.keys) n += kv.second.type != nullptr;
-    put_u64(out, n);
-    for (auto& kv : H.keys) {
-      if (!kv.second.type) continue;
-      IO io;
-      kv.second.type->m.rdb_save(&io, kv.second.value);
-      put_s(out, kv.first);
-      put_s(out, kv.second.type->name);
-      put_u64(out, (uint64_t)kv.second.type->encver);
-      put_s(out, io.buf);
-    }
-    std::ofstream f(w[1], std::ios::binary);
-    f.write(out.data(), (std::streamsize)out.size());
     r.kind = Reply::kInt;
-    r.i = (long long)n;
+    r.i = save_all(w[1]);
+  } else if (w[0] == "#BGSAVE" && w.size() == 2) {
+    fire_event(1 /* REDISMODULE_EVENT_PERSISTENCE */, 0 /* RDB_START */);
+    std::fflush(stdout);
+    pid_t pid = fork();
+    if (pid == 0) {
+      long long n = save_all(w[1]);
+      _exit(n >= 0 ? 0 : 1);  // no atexit handlers, no static destructors: like redis' child
+    }
+    int status = 0;
+    waitpid(pid, &status, 0);
+    fire_event(1, 4 /* ENDED on Redis >= 7.0 */);
+    if (pid < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) {
+      r.kind = Reply::kError;
+      r.s = "ERR background save failed";
+    } else {
+      r.kind = Reply::kStatus;
+      r.s = "Background saving done";
+    }
   } else if (w[0] == "#LOAD" && w.size() == 2) {
     std::ifstream f(w[1], std::ios::binary);
     std::stringstream ss;

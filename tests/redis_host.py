@@ -18,11 +18,13 @@ def fmt(v):
     return repr(float(v))
 
 
-def run(commands, timeout=600):
-    """commands: list of strings or lists of words.  Returns the list of decoded replies (same length)."""
+def run(commands, timeout=600, env=None):
+    """commands: list of strings or lists of words.  Returns the list of decoded replies (same length).
+    `env`: extra environment for the host process (e.g. FAKE_REDIS_NO_EVENTS=1)."""
     build()
     lines = [c if isinstance(c, str) else " ".join(str(w) for w in c) for c in commands]
-    p = subprocess.run([HOST, MODULE], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=timeout)
+    p = subprocess.run([HOST, MODULE], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=timeout,
+                       env=dict(os.environ, **(env or {})))
     assert p.returncode == 0, "fake_redis_host rc=%d stderr=%s" % (p.returncode, p.stderr[-2000:])
     out = [json.loads(l) for l in p.stdout.splitlines() if l.strip()]
     assert len(out) == len(lines), "expected %d replies, got %d\n%s" % (len(lines), len(out), p.stderr[-2000:])

@@ -153,3 +153,30 @@ def test_search_replies_equal_the_oracle_and_survive_an_rdb_round_trip(tmp_path)
     assert r2[base + 22][1][1] == -0.0 and r2[base + 22][1][3] == "e4"
     assert r2[base + 23] == 1 and r2[base + 24] == []
     os.remove(rdb)
+
+
+@pytest.mark.parametrize("events", [True, False])
+def test_bgsave_in_a_forked_child_sees_current_records(tmp_path, events):
+    """Redis writes RDB files from a fork()ed child, where the parent's CUDA context is unusable.  With server events the
+    module snapshots every record to host memory when the persistence event fires (before the fork); without them it keeps
+    the records current after every mutation, as the reference does (lib.rs:351-365).  Either way the child must write the
+    CURRENT graph: mutate after a first save, BGSAVE, load in a fresh process, compare against the parent's replies."""
+    n, dim, m, efc = 300, 32, 5, 48
+    x, q = data.uniform(n + 30, dim, seed=8, n_queries=10)
+    env = None if events else {"FAKE_REDIS_NO_EVENTS": "1"}
+    rdb1, rdb2 = str(tmp_path / "a.fake_rdb"), str(tmp_path / "b.fake_rdb")
+    probe = ["HNSW.GET idx"] + ["HNSW.NODE.GET idx n%d" % i for i in (0, 5, 17, n + 3, n + 29)] + \
+        ["HNSW.SEARCH idx K 10 QUERY %d %s" % (dim, _vec(v)) for v in q]
+    cmds = _build_cmds("idx", x[:n], m, efc) + ["#BGSAVE " + rdb1]
+    cmds += ["HNSW.NODE.ADD idx n%d DATA %d %s" % (i, dim, _vec(x[i])) for i in range(n, n + 30)]
+    cmds += ["HNSW.NODE.DEL idx n%d" % i for i in (7, 8, 9)]
+    cmds += ["#BGSAVE " + rdb2] + probe
+    r = R.run(cmds, env=env)
+    assert r[n + 1] == {"status": "Background saving done"}
+    assert r[n + 35] == {"status": "Background saving done"}
+    want = r[n + 36:]
+    got = R.run(["#LOAD " + rdb2] + probe)
+    assert got[0] == n + 30 - 3 + 1
+    assert got[1:] == want
+    first = R.run(["#LOAD " + rdb1, "HNSW.GET idx"])
+    assert first[0] == n + 1 and R.pairs(first[1])["node_count"] == n
