@@ -36,6 +36,7 @@ WORKLOADS = {
     "10Mx128_M16_efc200": (10_000_000, 128, 16, 200, "lowrank", 16),   # configs[3]
     "100Kx128_M16_efc200": (100_000, 128, 16, 200, "lowrank", 16),     # quick check
     "10Kx32_M5_efc100": (10_000, 32, 5, 100, "uniform", 0),            # configs[0]
+    "1Mx128_M16_efc200_uniform": (1_000_000, 128, 16, 200, "uniform", 0),   # stress dataset: intrinsic dim 128
 }
 
 

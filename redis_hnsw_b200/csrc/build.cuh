@@ -169,17 +169,21 @@ __device__ __forceinline__ void list_erase(uint32_t* buf, uint32_t len, int p, i
 
 // add_neighbor (core.rs:137-143) on the row of (node, level): append `x` unless present.
 // Returns the new length (kEmpty on failure).  Caller holds the row lock (FAST) or is the only writer (EXACT).
+// `full` (optional) is set when the list already holds `lcap` ids: the batched builder then drops the edge on both
+// sides (a hub row is bounded by the edit buffer); without it a full list raises the sticky kErrListTooLong flag.
 __device__ __forceinline__ uint32_t row_append_unique(const Graph& g, uint32_t node, uint32_t level, uint32_t x,
-                                                      uint32_t* buf, uint32_t lcap, int lane) {
+                                                      uint32_t* buf, uint32_t lcap, int lane, bool* full = nullptr) {
   uint32_t* ovf;
   uint32_t* row = row_ptr(g, node, level, &ovf);
+  if (full) *full = false;
   if (!row) return kEmpty;
   uint32_t len = list_load(g, row, ovf, buf, lcap, lane);
+  if (len != kEmpty && list_find(buf, len, x, lane) >= 0) return len;
   if (len == kEmpty || len + 1 > lcap) {
-    if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
+    if (full) *full = true;
+    else if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
     return kEmpty;
   }
-  if (list_find(buf, len, x, lane) >= 0) return len;
   if (lane == 0) buf[len] = x;
   __syncwarp();
   if (!list_store(g, row, ovf, buf, len + 1, lane)) return kEmpty;
@@ -680,12 +684,18 @@ __global__ void __launch_bounds__(256) build_link_kernel(Graph g, FastArgs a) {
       __syncwarp();
       list_store(g, row, ovf, edit, n_sel, lane);
     }
+    bool refused = false;  // some ids[i] is a hub whose list is full: that edge is dropped on both sides
     for (uint32_t i = 0; i < n_sel; ++i) {
       const uint32_t r = ids[i];
       const uint32_t key = row_key(g, r, lc);
       uint32_t* lk = lock_of(g, key);
       row_lock(lk, lane);
-      uint32_t len = row_append_unique(g, r, lc, q, edit, a.lcap, lane);
+      bool full;
+      uint32_t len = row_append_unique(g, r, lc, q, edit, a.lcap, lane, &full);
+      if (full) {
+        refused = true;
+        if (lane == 0) a.sel_ids[(size_t)t * a.m + i] = kEmpty;
+      }
       if (len != kEmpty && len > cap && lane == 0) {
         uint32_t* st = (key & 0x80000000u) ? a.stampU + (key & 0x7FFFFFFFu) : a.stamp0 + key;
         if (*reinterpret_cast<volatile uint32_t*>(st) != a.epoch) {   // protected by the row lock
@@ -696,6 +706,21 @@ __global__ void __launch_bounds__(256) build_link_kernel(Graph g, FastArgs a) {
         }
       }
       row_unlock(lk, lane);
+    }
+    if (refused) {  // rewrite q's own row without the refused hubs
+      uint32_t* ovf;
+      uint32_t* row = row_ptr(g, q, lc, &ovf);
+      uint32_t kept = 0;
+      __syncwarp();
+      if (lane == 0) {
+        for (uint32_t i = 0; i < n_sel; ++i) {
+          const uint32_t v = a.sel_ids[(size_t)t * a.m + i];
+          if (v != kEmpty) edit[kept++] = v;
+        }
+      }
+      kept = __shfl_sync(kFull, kept, 0);
+      __syncwarp();
+      list_store(g, row, ovf, edit, kept, lane);
     }
   }
 }
@@ -824,8 +849,14 @@ __global__ void __launch_bounds__(256) build_apply_kernel(Graph g, FastArgs a) {
       if (list_find(old, n_old, x, lane) >= 0) continue;
       uint32_t* lk = lock_of(g, row_key(g, x, lc));
       row_lock(lk, lane);
-      row_append_unique(g, x, lc, e, edit, a.lcap, lane);
+      bool full;
+      row_append_unique(g, x, lc, e, edit, a.lcap, lane, &full);
       row_unlock(lk, lane);
+      if (full) {  // x is a hub whose list is full: drop the edge on e's side too (keeps the graph symmetric)
+        row_lock(elock, lane);
+        row_remove(g, e, lc, x, edit, a.lcap, lane);
+        row_unlock(elock, lane);
+      }
     }
   }
 }

@@ -177,7 +177,7 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
     for (int lc = 0; lc <= top; ++lc) task_node.push_back(first + b), task_level.push_back((uint32_t)lc);
   }
   const uint32_t n_tasks = (uint32_t)task_node.size();
-  const uint32_t wl_cap = std::min<uint64_t>((uint64_t)n_tasks * m, 6ull * count + 1024);
+  const uint32_t wl_cap = std::min<uint64_t>((uint64_t)n_tasks * m, 10ull * count + 1024);
 
   // visited tables of K1 (same policy as the search path: shared memory when it fits)
   const uint32_t slots = next_pow2(std::max<uint64_t>(1024, (uint64_t)ef_construction * 32));
@@ -215,7 +215,7 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   {
     // Allocate once for the largest batch this add_batch call will reach (cudaMalloc / cudaFree of scratch that grows
     // with every batch of the ramp cost 30-800 ms each on the test box: profiles/r1d_build.md), lay out for this one.
-    const size_t hc = std::max<size_t>(count, build_hint), ht = hc + hc / 2 + 64, hw = 6 * hc + 1024;
+    const size_t hc = std::max<size_t>(count, build_hint), ht = hc + hc / 2 + 64, hw = 10 * hc + 1024;
     const size_t want = al((size_t)kCtlWords * 4) + 2 * al(hc * 4) + 3 * al(ht * 4) + al(ht * m * 4) + 2 * al(hw * 4) + al(hw * 8) +
                         al(hw * (size_t)lcap * 4) + al(hw * (size_t)W * 4);
     if ((rc = ensure_scratch(s_build, std::max(off, want)))) return rc;

@@ -20,7 +20,8 @@
 //   * Cold start (load_index -> make_index, lib.rs:229-315) rebuilds the device graph from the loaded records in one
 //     pass on the first command that touches the index.
 //   * Extensions (not in the reference): `EF ef` on HNSW.SEARCH (the reference always searches with ef_construction,
-//     core.rs:485) and HNSW.MSEARCH, a multi-query form that reaches the batched device path.
+//     core.rs:485), HNSW.MSEARCH (a multi-query form that reaches the batched device path) and HNSW.NODE.MADD (a
+//     NODE.ADD stream in one command, for bulk loads).
 //   * Conscious fixes: HNSW.NODE.DEL of a missing node replies an error (the reference panics: lib.rs:384 unwrap);
 //     deleting the index key by other means (DEL, FLUSHALL) also drops the cached index (the reference keeps a stale
 //     entry in INDICES).
@@ -286,7 +287,7 @@ struct Key {
 
 // ---------------------------------------------------------------- argument schemas (lib.rs:37-129)
 
-enum ArgKind { kU64, kF64Vec };
+enum ArgKind { kU64, kF64Vec, kStrVec };
 struct KwSpec {
   const char* name;
   ArgKind kind;
@@ -299,6 +300,7 @@ struct Parsed {
   std::map<std::string, uint64_t> u64s;
   std::map<std::string, std::vector<double>> vecs;
   std::map<std::string, uint64_t> vec_rows;  // matrix form: leading row count
+  std::map<std::string, std::vector<std::string>> strs;
 };
 
 std::string upper(std::string s) {
@@ -346,6 +348,13 @@ Parsed parse_args(const std::vector<std::string>& args, const char* cmd, size_t 
       if (i >= args.size() || !parse_u64(args[i], &v)) throw ReplyError{"ERR " + kw + " needs an unsigned integer"};
       p.u64s[kw] = v;
       ++i;
+    } else if (spec->kind == kStrVec) {
+      uint64_t n;
+      if (i >= args.size() || !parse_u64(args[i], &n)) throw ReplyError{"ERR " + kw + " needs a count followed by that many names"};
+      ++i;
+      if (n > args.size() - i) throw ReplyError{"ERR " + kw + " announces more names than were given"};
+      p.strs[kw] = std::vector<std::string>(args.begin() + (long)i, args.begin() + (long)(i + n));
+      i += n;
     } else {
       uint64_t rows = 1, n;
       if (matrix_kw && kw == matrix_kw) {
@@ -370,6 +379,7 @@ Parsed parse_args(const std::vector<std::string>& args, const char* cmd, size_t 
       p.u64s[k.name] = k.dflt;
     }
     if (k.kind == kF64Vec && !p.vecs.count(k.name) && k.required) throw ReplyError{std::string("ERR missing argument: ") + k.name};
+    if (k.kind == kStrVec && !p.strs.count(k.name) && k.required) throw ReplyError{std::string("ERR missing argument: ") + k.name};
   }
   return p;
 }
@@ -635,6 +645,31 @@ void cmd_msearch(RedisModuleCtx* ctx, const std::vector<std::string>& args) {
   for (const auto& r : res) reply_results(ctx, r);
 }
 
+// extension: HNSW.NODE.MADD {index} [FAST 0|1] NODES {n} {name1..namen} DATA {n} {dim} {n*dim values}
+// a NODE.ADD stream in one command (bulk load); FAST 1 (default) uses the batched device builder, FAST 0 the
+// sequentially consistent one.  Replies the number of nodes added.
+void cmd_node_madd(RedisModuleCtx* ctx, const std::vector<std::string>& args) {
+  Parsed p = parse_args(args, "hnsw.node.madd", 1,
+                        {{"FAST", kU64, false, 1}, {"NODES", kStrVec, true, 0}, {"DATA", kF64Vec, true, 0}}, "DATA");
+  const std::string index_name = std::string(PREFIX) + "." + p.pos[0];
+  const std::vector<std::string>& suffixes = p.strs["NODES"];
+  if (p.vec_rows["DATA"] != suffixes.size()) throw ReplyError{"ERR NODES and DATA announce different counts"};
+  std::vector<std::string> names;
+  names.reserve(suffixes.size());
+  for (const std::string& sfx : suffixes) names.push_back(index_name + "." + sfx);
+  std::vector<float> data = narrow(p.vecs["DATA"]);
+  auto ix = load_index(ctx, index_name);
+  try {
+    ix->add_nodes(names, data.data(), p.u64s["DATA.N"], p.u64s["FAST"] != 0);
+  } catch (const HNSWError& e) {
+    throw ReplyError{error_string(e.what())};
+  }
+  for (const std::string& nn : names) write_node(ctx, nn, ix);
+  if (g_eager) materialize(index_name, ix);  // a batch touches too many rows to refresh one by one: snapshot them all
+  update_index(ctx, index_name, ix);
+  RedisModule_ReplyWithLongLong(ctx, (long long)names.size());
+}
+
 typedef void (*Handler)(RedisModuleCtx*, const std::vector<std::string>&);
 
 template <Handler H>
@@ -679,6 +714,7 @@ extern "C" int RedisModule_OnLoad(RedisModuleCtx* ctx, RedisModuleString** argv,
       {"hnsw.del", command<cmd_del>, "write"},           {"hnsw.search", command<cmd_search>, "readonly"},
       {"hnsw.node.add", command<cmd_node_add>, "write"}, {"hnsw.node.get", command<cmd_node_get>, "readonly"},
       {"hnsw.node.del", command<cmd_node_del>, "write"}, {"hnsw.msearch", command<cmd_msearch>, "readonly"},
+      {"hnsw.node.madd", command<cmd_node_madd>, "write"},
   };
   for (const auto& c : cmds)
     if (RedisModule_CreateCommand(ctx, c.name, c.fn, c.flags, 0, 0, 0) != REDISMODULE_OK) return REDISMODULE_ERR;

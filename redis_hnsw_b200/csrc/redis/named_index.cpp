@@ -87,6 +87,26 @@ void NamedIndex::add_node(const std::string& node_name, const float* data, size_
   if (touched) *touched = touched_names();  // core.rs:580-584
 }
 
+void NamedIndex::add_nodes(const std::vector<std::string>& node_names, const float* data, size_t n, bool fast) {
+  if (n != dim_)
+    throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
+  if (node_names.empty()) return;
+  {
+    std::unordered_map<std::string, int> seen;
+    for (const std::string& nn : node_names)
+      if (ids_.count(nn) || seen[nn]++) throw HNSWError("Node: " + rust_debug_str(nn) + " already exists", HNSW_ERR_EXISTS);
+  }
+  uint32_t first = 0;
+  check(hnsw_index_add_batch(h_, node_names.size(), data, nullptr, fast ? HNSW_BUILD_FAST : HNSW_BUILD_EXACT, &first));
+  if (first != names_.size()) throw HNSWError("device id out of sequence");
+  for (size_t i = 0; i < node_names.size(); ++i) {
+    names_.push_back(node_names[i]);
+    alive_.push_back(1);
+    ids_[node_names[i]] = first + (uint32_t)i;
+  }
+  ++epoch_;
+}
+
 void NamedIndex::delete_node(const std::string& node_name, std::vector<std::string>* touched) {
   auto it = ids_.find(node_name);
   if (it == ids_.end())  // core.rs:419-422

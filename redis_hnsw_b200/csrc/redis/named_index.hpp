@@ -63,6 +63,10 @@ class NamedIndex {
   // (core.rs:580-584).  `level` >= 0 injects the level draw (tests); -1 draws.
   void add_node(const std::string& node_name, const float* data, size_t n, std::vector<std::string>* touched = nullptr,
                 int level = -1);
+  // extension: a NODE.ADD stream of `count` nodes in one call (hnsw_index_add_batch).  fast = true uses the batched
+  // builder (HNSW_BUILD_FAST: same per-insert algorithm, nodes of one batch do not see each other); false is the
+  // sequentially consistent stream.  All names are checked before anything is inserted.
+  void add_nodes(const std::vector<std::string>& node_names, const float* data, size_t n, bool fast);
   // core.rs:414-475
   void delete_node(const std::string& node_name, std::vector<std::string>* touched = nullptr);
   // core.rs:477-486 (ef = 0 -> ef_construction, core.rs:485)

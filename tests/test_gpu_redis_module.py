@@ -180,3 +180,30 @@ def test_bgsave_in_a_forked_child_sees_current_records(tmp_path, events):
     assert got[1:] == want
     first = R.run(["#LOAD " + rdb1, "HNSW.GET idx"])
     assert first[0] == n + 1 and R.pairs(first[1])["node_count"] == n
+
+
+@pytest.mark.parametrize("fast,events", [(1, True), (0, True), (1, False)])
+def test_node_madd_bulk_load(tmp_path, fast, events):
+    """HNSW.NODE.MADD (extension): a NODE.ADD stream in one command.  FAST 0 must give the graph of the one-by-one stream
+    when the levels are the same — the engine draws them from the same generator in both cases — and every form must
+    leave a consistent keyspace that survives BGSAVE + reload."""
+    n, dim, m, efc = 400, 32, 5, 48
+    x, q = data.uniform(n, dim, seed=21, n_queries=8)
+    env = None if events else {"FAKE_REDIS_NO_EVENTS": "1"}
+    rdb = str(tmp_path / "m.fake_rdb")
+    madd = "HNSW.NODE.MADD idx FAST %d NODES %d %s DATA %d %d %s" % (
+        fast, n - 1, " ".join("n%d" % i for i in range(1, n)), n - 1, dim, " ".join(_vec(v) for v in x[1:]))
+    probe = ["HNSW.GET idx"] + ["HNSW.NODE.GET idx n%d" % i for i in (0, 1, 77, n - 1)] + \
+        ["HNSW.SEARCH idx K 5 EF 48 QUERY %d %s" % (dim, _vec(v)) for v in q]
+    cmds = ["HNSW.NEW idx DIM %d M %d EFCON %d" % (dim, m, efc), "HNSW.NODE.ADD idx n0 DATA %d %s" % (dim, _vec(x[0])), madd,
+            "HNSW.NODE.MADD idx NODES 1 n5 DATA 1 %d %s" % (dim, _vec(x[5])), "#KEYS", "#BGSAVE " + rdb] + probe
+    r = R.run(cmds, env=env)
+    assert r[2] == n - 1
+    assert r[3] == {"error": 'String("Node: \\"hnsw.idx.n5\\" already exists")'}
+    assert len(r[4]) == n + 1
+    assert R.pairs(r[6])["node_count"] == n
+    got = R.run(["#LOAD " + rdb] + probe)
+    assert got[0] == n + 1 and got[1:] == r[6:]
+    if fast == 0:                                                  # same levels, same order -> same graph as one-by-one
+        one = R.run(_build_cmds("idx", x, m, efc) + probe)
+        assert one[n + 1:] == r[6:]

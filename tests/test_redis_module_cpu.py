@@ -12,7 +12,7 @@ def test_onload_registers_the_reference_command_table():
            "hnsw.node.add": "write", "hnsw.node.get": "readonly", "hnsw.node.del": "write"}   # lib.rs:505-513
     for cmd, flags in ref.items():
         assert table[cmd] == (flags, 0, 0, 0), cmd
-    assert set(table) - set(ref) == {"hnsw.msearch"}                            # the one labelled extension
+    assert set(table) - set(ref) == {"hnsw.msearch", "hnsw.node.madd"}          # the labelled extensions
     assert sorted(types) == [["hnswindex", 0], ["hnswnodet", 0]]                # types.rs:13-14,157,354
 
 
