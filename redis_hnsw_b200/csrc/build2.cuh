@@ -209,8 +209,11 @@ __device__ __forceinline__ void apply_reselection(const Graph& g, const CandList
 }
 
 // core.rs:383-412 + 489-599, one warp, the NODE.ADD stream in order (see insert_exact_kernel)
-template <int EFR, int C>
+// SMALL: the re-selection list (<= m_max_0 entries) lives in min(EFR, 2) registers per lane instead of EFR, which cuts
+// the per-candidate list maintenance of the 2-hop sweeps by EFR/2 (the host picks it when m_max_0 <= 64).
+template <int EFR, int C, bool SMALL>
 __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a) {
+  constexpr int ER = SMALL ? (EFR < 2 ? EFR : 2) : EFR;
   constexpr int S = ExactStage<C>::S;
   using T = uint32_t;
   extern __shared__ __align__(128) unsigned char smem2[];
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a)
   uint32_t* edit = rem + a.lcap;
 
   CandList<EFR> L;
+  CandList<ER> R;
   Counters cnt = {0, 0, 0};
   uint32_t n_touched = 0, n_reprunes = 0;
   auto touch = [&](uint32_t id) {
@@ -274,9 +278,9 @@ __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a)
         }
         if (n_old <= cap) continue;                               // core.rs:561
         load_q_from_slab<C, S, T>(w, g, e, lane);
-        reprune_select2<EFR, C, S, T>(g, w, e, (uint32_t)lc, (int)cap, old, n_old, L, cnt, lane, kEmpty, keep_add);   // :568
+        reprune_select2<ER, C, S, T>(g, w, e, (uint32_t)lc, (int)cap, old, n_old, R, cnt, lane, kEmpty, keep_add);   // :568
         ++n_reprunes;
-        apply_reselection<EFR>(g, L, e, (uint32_t)lc, erow, eovf, old, n_old, keep_add, rem, edit, a.lcap, kEmpty, touch, lane);
+        apply_reselection<ER>(g, R, e, (uint32_t)lc, erow, eovf, old, n_old, keep_add, rem, edit, a.lcap, kEmpty, touch, lane);
       }
     }
     if (l > l_max && lane == 0) {                                 // core.rs:587-593

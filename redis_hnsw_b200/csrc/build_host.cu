@@ -99,7 +99,8 @@ int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
   a.touched_cap = touched_cap;
   size_t smem = ((size_t)((m + 31) & ~31u) + 4 * (size_t)lcap + g.W) * 4 + (kind_needs_smem_query(kind) ? (size_t)dim * 4 : 0);
   int kern = kKernExact;
-  if (exact_staged(&smem, ((size_t)((m + 31) & ~31u) + 4 * (size_t)lcap + g.W) * 4, &a.vis_slots)) kern = kKernExact2;
+  if (exact_staged(&smem, ((size_t)((m + 31) & ~31u) + 4 * (size_t)lcap + g.W) * 4, &a.vis_slots))
+    kern = m_max_0 <= 64 ? kKernExact2Small : kKernExact2;  // Small: re-selection lists of <= 64 entries in 2 registers
   LaunchCfg c{1, 32, smem, stream};
   e = run(kind, kern, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "insert_exact launch");
@@ -318,10 +319,11 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
     const int w = blk / 32;
     const size_t smem3 = (size_t)w * ((size_t)(rslots + lcap) * 4 + qs);
     if (smem3 > max_smem) return fail(HNSW_ERR_INVALID, "m too large for the re-selection kernel");
-    int occ3 = occupancy(kind, kKernBuildReprune, efr, blk, smem3);
+    const int efr3 = efr_for(m_max_0);  // the re-selected list holds at most m_max_0 entries: a short register list
+    int occ3 = occupancy(kind, kKernBuildReprune, efr3, blk, smem3);
     if (occ3 < 1) return fail(HNSW_ERR_CUDA, "re-selection kernel cannot be resident");
     LaunchCfg c{(int)std::min<uint64_t>((uint64_t)num_sms * occ3, (wl_cap + w - 1) / w), blk, smem3, stream};
-    e = run(kind, kKernBuildReprune, efr, c, g, &a3);
+    e = run(kind, kKernBuildReprune, efr3, c, g, &a3);
     if (e != cudaSuccess) return cuda_fail(e, "build_reprune launch");
   }
   tr.mark(3);
@@ -391,7 +393,7 @@ int Index::add_fast(uint32_t first, uint32_t count) {
 
 int Index::delete_node(uint32_t id) {
   if (id >= n_ids || h_level[id] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", id);  // core.rs:421
-  const int efr = build_efr(*this);
+  const int efr = efr_for(m_max_0);  // delete only re-selects lists of at most m_max_0 entries
   if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
   int rc = pull_meta();  // the device owns pool_used
   if (rc) return rc;
