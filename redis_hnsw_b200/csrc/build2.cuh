@@ -19,7 +19,7 @@ struct BuildStage {
 };
 
 template <int EFR, int C, class T>
-__global__ void __launch_bounds__(256) build_search2_kernel(Graph g, FastArgs a) {
+__global__ void __launch_bounds__(128, Search2Bounds<EFR>::kMinBlocks) build_search2_kernel(Graph g, FastArgs a) {
   constexpr int S = BuildStage<C>::S;
   constexpr int V = RowRegs<C>::V;
   extern __shared__ __align__(128) unsigned char smem2[];

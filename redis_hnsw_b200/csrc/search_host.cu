@@ -151,7 +151,7 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   // 16-bit tags identify an id exactly only below 2^(log2(slots) + 15)
   const bool tag16 = opt_recent_tag != 32 && slot_bits + 15 < 32 && n_ids <= (1ull << (slot_bits + 15));
   const size_t per_warp = warp2_smem_bytes(dim, S, slots, tag16 ? 2 : 4);
-  int block = opt_block ? opt_block : 64;
+  int block = opt_block ? std::min(opt_block, 128) : 64;  // search_knn2_kernel is bounded at 128 threads per CTA
   while (block > 32 && (size_t)(block / 32) * per_warp > max_smem) block /= 2;
   const int warps = block / 32;
   const size_t smem = (size_t)warps * per_warp;
