@@ -19,7 +19,7 @@ struct BuildStage {
 };
 
 template <int EFR, int C, class T>
-__global__ void __launch_bounds__(128, Search2Bounds<EFR>::kMinBlocks) build_search2_kernel(Graph g, FastArgs a) {
+__global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) build_search2_kernel(Graph g, FastArgs a) {
   constexpr int S = BuildStage<C>::S;
   constexpr int V = RowRegs<C>::V;
   extern __shared__ __align__(128) unsigned char smem2[];
@@ -369,6 +369,64 @@ __global__ void __launch_bounds__(32) delete_exact2_kernel(Graph g, ExactArgs a)
     a.ctl[kCtlDistEvals] += cnt.n_dist;
     a.ctl[kCtlReprunes] += n_reprunes;
     a.ctl[kCtlTouched] = n_touched;
+  }
+}
+
+}  // namespace hnsw
+
+// ================================================================ K3 of the batched builder on the staged machinery
+//
+// build_reprune_kernel (build.cuh) with reprune_select2: unseen ids are collected across the rows of a 2-hop sweep and
+// evaluated a full stage at a time.  Same worklist protocol, same outputs (wl_old / wl_new / wl_len).
+namespace hnsw {
+
+template <int EFR, int C, class T>
+__global__ void __launch_bounds__(128, (C > 8 ? 4 : 6)) build_reprune2_kernel(Graph g, FastArgs a) {
+  constexpr int S = BuildStage<C>::S;
+  extern __shared__ __align__(128) unsigned char smem2[];
+  const int lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  // per warp: Warp2 region | old[lcap] | pend[64]
+  const size_t per_warp = warp2_smem_bytes(32 * C, S, a.vis_slots, sizeof(T)) + ((size_t)a.lcap + 64) * 4;
+  unsigned char* base = smem2 + (size_t)warp * per_warp;
+  Warp2<C, S, T> w;
+  uint32_t* old = reinterpret_cast<uint32_t*>(warp2_setup<C, S, T>(w, base, a.vis_slots, lane));
+  uint32_t* pend = old + a.lcap;
+  const uint32_t total = min(a.ctl[kCtlWlCount], a.wl_cap);
+  CandList<EFR> L;
+  Counters cnt = {0, 0, 0};
+  uint32_t n_done = 0, n_skip = 0;
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(a.ctl + kCtlWorkReprune, 1u);
+    wi = __shfl_sync(kFull, wi, 0);
+    if (wi >= total) break;
+    const uint32_t e = a.wl_node[wi], lc = a.wl_level[wi];
+    const uint32_t cap = lc == 0 ? a.cap0 : a.capU;
+    uint32_t* ovf;
+    uint32_t* row = row_ptr(g, e, lc, &ovf);
+    const uint32_t n_old = list_load(g, row, ovf, old, a.lcap, lane);
+    if (n_old == kEmpty) {
+      if (lane == 0) a.wl_len[2 * wi] = 0, a.wl_len[2 * wi + 1] = kEmpty;
+      ++n_skip;
+      continue;
+    }
+    load_q_from_slab<C, S, T>(w, g, e, lane);
+    reprune_select2<EFR, C, S, T>(g, w, e, lc, (int)cap, old, n_old, L, cnt, lane, kEmpty, pend);
+    ++n_done;
+    for (uint32_t i = lane; i < n_old; i += 32) a.wl_old[(size_t)wi * a.lcap + i] = old[i];
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) {
+      int p = r * 32 + lane;
+      if (p < L.len) a.wl_new[(size_t)wi * g.W + p] = L.id[r] & ~kExpanded;
+    }
+    if (lane == 0) a.wl_len[2 * wi] = n_old, a.wl_len[2 * wi + 1] = (uint32_t)L.len;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd(a.ctl + kCtlDistEvals, cnt.n_dist);
+    atomicAdd(a.ctl + kCtlReprunes, n_done);
+    atomicAdd(a.ctl + kCtlSkipped, n_skip);
   }
 }
 

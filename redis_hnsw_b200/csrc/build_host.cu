@@ -308,7 +308,32 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   }
   tr.mark(2);
   // K3
-  {
+  bool staged3 = staged;
+  if (staged3) {  // re-selection on the staged machinery (build_reprune2_kernel)
+    const int S = dim == 32 ? 32 : (dim <= 128 ? 8 : 4);  // BuildStage<C>::S
+    const uint32_t vslots = next_pow2(std::max<uint64_t>(1024, (uint64_t)m_max_0 * 64));
+    int vbits = 0;
+    while ((1u << vbits) < vslots) ++vbits;
+    const bool tag16 = vbits + 15 < 32 && n_ids <= (1ull << (vbits + 15));
+    const size_t per_warp = warp2_smem_bytes(dim, S, vslots, tag16 ? 2 : 4) + ((size_t)lcap + 64) * 4;
+    int blk = 64;
+    while (blk > 32 && (size_t)(blk / 32) * per_warp > max_smem) blk /= 2;
+    const int w3 = blk / 32;
+    const size_t smem3 = (size_t)w3 * per_warp;
+    const int efr3 = efr_for(m_max_0);
+    const int id3 = kKernBuildReprune2 + (tag16 ? 1 : 0);
+    const int occ3 = smem3 <= max_smem ? occupancy(kind, id3, efr3, blk, smem3) : 0;
+    if (occ3 < 1) {
+      staged3 = false;
+    } else {
+      FastArgs a3 = a;
+      a3.vis_slots = vslots;
+      LaunchCfg c{(int)std::min<uint64_t>((uint64_t)num_sms * occ3, (wl_cap + w3 - 1) / w3), blk, smem3, stream};
+      e = run(kind, id3, efr3, c, g, &a3);
+      if (e != cudaSuccess) return cuda_fail(e, "build_reprune2 launch");
+    }
+  }
+  if (!staged3) {
     const uint32_t cap = m_max_0;
     // lossy direct-mapped table (expand_chunk_lossy): any size is correct, a larger one saves re-evaluations
     const uint32_t rslots = next_pow2(std::max<uint64_t>(1024, (uint64_t)cap * 64));

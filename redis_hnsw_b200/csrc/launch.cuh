@@ -43,7 +43,8 @@ enum KernelId : int {
 constexpr int kKernBuildSearch2 = 32;
 constexpr int kKernExact2 = 40;   // insert_exact2_kernel / delete_exact2_kernel (TMA-staged, build2.cuh)
 constexpr int kKernDelete2 = 41;
-constexpr int kKernExact2Small = 42;  // same, the re-selection list is CandList<min(EFR, 2)> (m_max_0 <= 64)
+constexpr int kKernExact2Small = 42;
+constexpr int kKernBuildReprune2 = 44;  // build_reprune2_kernel: + (16-bit visited tags ? 1 : 0)  // same, the re-selection list is CandList<min(EFR, 2)> (m_max_0 <= 64)
 inline int search2_id(int S, bool tag16) { return kKernSearch2 + 2 * (S == 4 ? 0 : S == 8 ? 1 : S == 16 ? 2 : 3) + (tag16 ? 1 : 0); }
 
 // kernel arguments are passed type-erased so that one entry point per kind serves every kernel
@@ -109,6 +110,8 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
       case kKernSearch2 + 7: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t>), SearchArgs)
       case kKernBuildSearch2 + 0: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
       case kKernBuildSearch2 + 1: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint16_t>), FastArgs)
+      case kKernBuildReprune2 + 0: HNSW_RUN((build_reprune2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
+      case kKernBuildReprune2 + 1: HNSW_RUN((build_reprune2_kernel<EFR, Dist::C, uint16_t>), FastArgs)
       case kKernExact2: HNSW_RUN((insert_exact2_kernel<EFR, Dist::C, false>), ExactArgs)
       case kKernExact2Small: HNSW_RUN((insert_exact2_kernel<EFR, Dist::C, true>), ExactArgs)
       case kKernDelete2: HNSW_RUN((delete_exact2_kernel<EFR, Dist::C>), ExactArgs)

@@ -282,14 +282,16 @@ __host__ __device__ inline size_t warp2_smem_bytes(uint32_t dim, int S, uint32_t
 // core.rs:477-486, 865-892
 // Register budget per list size: the kernel's throughput follows resident warps (profiles/tune_r1.md,
 // profiles/r1d_curve.md), and without a cap ptxas takes 105 / 120 registers for 8 / 16 list registers per lane.
-// __launch_bounds__(128, B) caps registers at 65536 / (128 * B): 64 for B = 8, 72 for 7, 80 for 6, 96 for 5.
-template <int EFR>
+// __launch_bounds__(128, B) caps registers at 65536 / (128 * B): 64 for B = 8, 72 for 7, 80 for 6, 128 for 4.
+// Rows of 768 floats (C = 24) keep 24 query registers per lane and are bandwidth/power-bound with few warps: a cap
+// there only adds spills (measured: 256 k -> 232 k QPS at 1M x 768, ef = 200), so large C keeps 128 registers.
+template <int EFR, int C = 4>
 struct Search2Bounds {
-  static constexpr int kMinBlocks = EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6);
+  static constexpr int kMinBlocks = C > 8 ? 4 : (EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6));
 };
 
 template <int EFR, int C, int S, class T>
-__global__ void __launch_bounds__(128, Search2Bounds<EFR>::kMinBlocks) search_knn2_kernel(Graph g, SearchArgs a) {
+__global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) search_knn2_kernel(Graph g, SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem2[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
