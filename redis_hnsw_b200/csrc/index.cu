@@ -196,6 +196,8 @@ Index::~Index() {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
+  for (cudaStream_t a : aux_stream)
+    if (a) cudaStreamDestroy(a);
 }
 
 // ---------------------------------------------------------------- Index: vectors

@@ -93,8 +93,12 @@ struct Index {
   int search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
                         uint32_t* n_out);
   uint32_t pick_vis_slots(uint32_t ef);
+  static constexpr uint32_t kCtlSlots = 8;  // 64-byte control slots for concurrently running search launches
   int search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef, int efr, uint32_t* d_ids, float* d_sims,
-                     uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s);
+                     uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s, uint32_t ctl_slot = 0);
+  int search_host_pipelined(uint64_t nq, const float* q, uint32_t k, uint32_t ef, int efr, uint32_t* ids, float* sims,
+                            uint32_t* counts, const float* d_q, uint32_t* d_ids, float* d_sims, uint32_t* d_counts);
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
 
   // insert (build_host.cu)
   int add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id, bool want_touched);

@@ -137,7 +137,7 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
 
 // TMA-staged kernel (search2.cuh): no retry pass (its visited table cannot overflow)
 int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef, int efr, uint32_t* d_ids, float* d_sims,
-                          uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s) {
+                          uint32_t* d_counts, uint32_t* d_stats, cudaStream_t s, uint32_t ctl_slot) {
   int S = opt_stage_rows;
   if (!S) {
     // about 4 KB of rows in flight per warp: on a B200 the kernel is occupancy-hungry (measured, profiles/), many
@@ -161,9 +161,10 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   if (occ < 1) return fail(HNSW_ERR_CUDA, "staged search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
   const int grid = (int)std::min<uint64_t>((uint64_t)num_sms * occ, (nq + warps - 1) / warps);
-  int rc = ensure_scratch(s_ctl, 64 + (size_t)nq * 4);
+  // control words: one 64-byte slot per concurrently running launch (search_host pipelines chunks on two streams)
+  int rc = ensure_scratch(s_ctl, std::max<size_t>(64 + (size_t)nq * 4, 64 * kCtlSlots));
   if (rc) return rc;
-  uint32_t* ctl = (uint32_t*)s_ctl.p;
+  uint32_t* ctl = (uint32_t*)s_ctl.p + (size_t)(ctl_slot % kCtlSlots) * 16;
   cudaError_t e = cudaMemsetAsync(ctl, 0, 64, s);
   if (e != cudaSuccess) return cuda_fail(e, "search ctl memset");
   SearchArgs a{};
@@ -184,6 +185,42 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   return HNSW_OK;
 }
 
+// Host-buffer batches on the staged kernel are pipelined: the batch is cut into chunks that alternate between two
+// streams, so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernel of chunk i (pinned host
+// memory; pageable memory still works, the copies then serialise).
+int Index::search_host_pipelined(uint64_t nq, const float* q, uint32_t k, uint32_t ef, int efr, uint32_t* ids, float* sims,
+                                 uint32_t* counts, const float* d_q, uint32_t* d_ids, float* d_sims, uint32_t* d_counts) {
+  for (int i = 0; i < 2; ++i)
+    if (!aux_stream[i]) {
+      cudaError_t e = cudaStreamCreateWithFlags(&aux_stream[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return cuda_fail(e, "aux stream");
+    }
+  const uint64_t n_chunks = std::min<uint64_t>(kCtlSlots, std::max<uint64_t>(2, nq / 16384));
+  const uint64_t per = (nq + n_chunks - 1) / n_chunks;
+  // size the control scratch before anything is in flight (ensure_scratch may reallocate)
+  int rc = ensure_scratch(s_ctl, std::max<size_t>(64 + (size_t)nq * 4, 64 * kCtlSlots));
+  if (rc) return rc;
+  cudaError_t e = cudaSuccess;
+  for (uint64_t c = 0, lo = 0; lo < nq; ++c, lo += per) {
+    const uint64_t n = std::min(per, nq - lo);
+    cudaStream_t st = aux_stream[c & 1];
+    e = cudaMemcpyAsync((float*)d_q + lo * dim, q + lo * dim, n * dim * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "query H2D");
+    if ((rc = search_device2(n, d_q + lo * dim, k, ef, efr, d_ids + lo * k, d_sims + lo * k, d_counts + lo, nullptr, st,
+                             (uint32_t)c)))
+      return rc;
+    e = cudaMemcpyAsync(ids + lo * k, d_ids + lo * k, n * k * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sims + lo * k, d_sims + lo * k, n * k * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts + lo, d_counts + lo, n * 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "result D2H");
+  }
+  for (int i = 0; i < 2; ++i) {
+    e = cudaStreamSynchronize(aux_stream[i]);
+    if (e != cudaSuccess) return cuda_fail(e, "search_batch");
+  }
+  return HNSW_OK;
+}
+
 int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uint32_t* ids, float* sims,
                        uint32_t* counts, uint32_t* stats) {
   if (nq == 0) return HNSW_OK;
@@ -199,6 +236,16 @@ int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uin
   float* d_sims = (float*)(o + al(ib));
   uint32_t* d_counts = (uint32_t*)(o + 2 * al(ib));
   uint32_t* d_stats = stats ? (uint32_t*)(o + 2 * al(ib) + al(cb)) : nullptr;
+  {
+    const uint32_t ef_eff = ef ? ef : ef_construction;
+    const int efr = efr_for(ef_eff);
+    const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
+    if (!stats && nq >= 8192 && efr && staged_kind && opt_search_impl != 1 && nq <= 0x7FFFFFFFull) {
+      if ((rc = search_host_pipelined(nq, q, k, ef_eff, efr, ids, sims, counts, (const float*)s_in.p, d_ids, d_sims, d_counts)))
+        return rc;
+      return pull_meta();
+    }
+  }
   cudaError_t e = cudaMemcpyAsync(s_in.p, q, qb, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return cuda_fail(e, "query H2D");
   if ((rc = search_device(nq, (const float*)s_in.p, k, ef, d_ids, d_sims, d_counts, d_stats, stream))) return rc;

@@ -13,6 +13,9 @@ CASES = {
     "d768_m32": (1200, 768, 32, 120, "lowrank32", 300),           # configs[2] shape, small N / efCon
     "d96_m8_generic": (3000, 96, 8, 64, "uniform", 500),          # dim % 32 == 0 without a specialised kernel
     "d20_m6_scalar": (2000, 20, 6, 48, "uniform", 500),           # dim % 32 != 0 -> reference scalar path
+    "d64_m6_generic_v2": (2000, 64, 6, 48, "uniform", 400),       # generic kind, 2-wide row loads (dim/32 % 4 == 2)
+    "d256_m12_generic_v4": (1500, 256, 12, 64, "lowrank16", 300),  # generic kind, 4-wide row loads
+    "d33_m4_scalar": (800, 33, 4, 24, "uniform", 200),            # the reference's own non-x32 KAT dimension (metrics_tests.rs:28)
 }
 
 

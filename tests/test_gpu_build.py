@@ -41,6 +41,9 @@ def _assert_same_graph(gd, go):
     ("d768_m32", 500),           # configs[2] shape
     ("d96_m8_generic", 1500),
     ("d20_m6_scalar", 1200),
+    ("d64_m6_generic_v2", 1200),
+    ("d256_m12_generic_v4", 900),
+    ("d33_m4_scalar", 800),
 ])
 def test_exact_build_equals_oracle_graph(name, n):
     import redis_hnsw_b200 as r

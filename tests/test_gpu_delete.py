@@ -38,6 +38,8 @@ def _fresh(name, n):
     ("d768_m32", 300, 12),
     ("d96_m8_generic", 800, 40),
     ("d20_m6_scalar", 800, 40),
+    ("d64_m6_generic_v2", 700, 30),
+    ("d256_m12_generic_v4", 500, 20),
 ])
 def test_delete_equals_oracle(name, n, n_del):
     orc, dev, x, q, levels, m = _fresh(name, n)

@@ -14,6 +14,9 @@ from gpu_fixtures import CASES, assert_search_parity, case, device_index  # noqa
     ("d768_m32", (16, 128, 400)),
     ("d96_m8_generic", (16, 64, 200)),
     ("d20_m6_scalar", (16, 48, 100)),
+    ("d64_m6_generic_v2", (1, 16, 64, 100)),
+    ("d256_m12_generic_v4", (10, 64, 256)),
+    ("d33_m4_scalar", (8, 24, 64)),
 ])
 def test_search_parity(name, efs):
     c = case(name)
