@@ -307,7 +307,7 @@ int Index::load_graph(uint64_t n, const float* vectors, const int32_t* levels, c
   if (e == cudaSuccess) e = cudaMemsetAsync(g.ovfU, 0xFF, (size_t)cap_upper * 4, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(g.pool, 0xFF, (size_t)g.pool_cap * 32 * 4, stream);
 #define UP(dst, vec, cnt)                                                                                 \
-  if (e == cudaSuccess && (cnt))                                                                          \
+  if (e == cudaSuccess && (cnt) != 0)                                                                     \
     e = cudaMemcpyAsync(dst, vec.data(), (size_t)(cnt) * sizeof(vec[0]), cudaMemcpyHostToDevice, stream);
   UP(g.adj0, adj0, n * W)
   UP(g.ovf0, ovf0, n)
