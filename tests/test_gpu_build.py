@@ -37,7 +37,7 @@ def _assert_same_graph(gd, go):
 
 @pytest.mark.parametrize("name,n", [
     ("cfg1_10k_d32_m5", 4000),   # BASELINE configs[0] parameters
-    ("d128_m16", 2500),          # configs[1] parameters
+    ("d128_m16", 6000),          # configs[1] parameters
     ("d768_m32", 500),           # configs[2] shape
     ("d96_m8_generic", 1500),
     ("d20_m6_scalar", 1200),
