@@ -20,6 +20,10 @@ for dim, m, efc in ((128, 16, 64), (32, 5, 40), (20, 6, 32), (96, 8, 32)):
     ids, sims, cnt, st = dev.search_batch(q, 10, ef=48, stats=True)
     ids2, sims2, cnt2 = dev.search_batch(q, 10, ef=48)
     assert np.array_equal(ids, ids2)
+    if dim == 128:   # host batches >= 8192 queries take the two-stream pipelined path
+        big = np.tile(q, (128, 1))
+        ib, sb, cb = dev.search_batch(big, 10, ef=48)
+        assert np.array_equal(ib[:64], ids) and np.array_equal(ib[-64:], ids)
     dev.search(q[0], 5)
     dev.search_level(q[0], int(dev.params()["enterpoint"]), 8, 0)
     for v in (3, 700, int(dev.params()["enterpoint"]), 1499):
