@@ -193,6 +193,7 @@ Index::~Index() {
   void* ptrs[] = {g.vecs, g.adj0, g.ovf0, g.upper_base, g.level, g.adjU, g.ovfU, g.pool, g.meta, g.locks,
                   d_stamp0, d_stampU, s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p, s_bvis.p};
   if (h_retry_seen) cudaFreeHost(h_retry_seen);
+  if (h_stage) cudaFreeHost(h_stage);
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);

@@ -99,6 +99,9 @@ struct Index {
   int search_host_pipelined(uint64_t nq, const float* q, uint32_t k, uint32_t ef, int efr, uint32_t* ids, float* sims,
                             uint32_t* counts, const float* d_q, uint32_t* d_ids, float* d_sims, uint32_t* d_counts);
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  static constexpr size_t kPinnedStage = 128 * 1024;
+  char* h_stage = nullptr;          // pinned staging buffer for small host calls
+  bool last_search_staged = false;  // set by search_device: which kernel family served the last call
 
   // insert (build_host.cu)
   int add_batch(uint64_t count, const float* data, const int32_t* levels, int mode, uint32_t* first_id, bool want_touched);

@@ -125,7 +125,7 @@ static std::string last_segment(const std::string& full) {  // core.rs:885-887
   return p == std::string::npos ? full : full.substr(p + 1);
 }
 
-std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_t k, uint32_t ef) const {
+std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_t k, uint32_t ef, bool with_data) const {
   if (n != dim_)  // core.rs:478-480
     throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
   std::vector<SearchResult> out;
@@ -139,8 +139,10 @@ std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_
     SearchResult r;
     r.sim = sims[i];
     r.name = last_segment(names_[ids[i]]);
-    r.data.resize(dim_);
-    check(hnsw_index_node_vector(h_, ids[i], r.data.data()));  // core.rs:888 copies the stored vector
+    if (with_data) {
+      r.data.resize(dim_);
+      check(hnsw_index_node_vector(h_, ids[i], r.data.data()));  // core.rs:888 copies the stored vector
+    }
     out.push_back(std::move(r));
   }
   return out;

@@ -69,8 +69,10 @@ class NamedIndex {
   void add_nodes(const std::vector<std::string>& node_names, const float* data, size_t n, bool fast);
   // core.rs:414-475
   void delete_node(const std::string& node_name, std::vector<std::string>* touched = nullptr);
-  // core.rs:477-486 (ef = 0 -> ef_construction, core.rs:485)
-  std::vector<SearchResult> search_knn(const float* q, size_t n, size_t k, uint32_t ef = 0) const;
+  // core.rs:477-486 (ef = 0 -> ef_construction, core.rs:485).  The reference copies each hit's vector into the result
+  // (core.rs:888) but its HNSW.SEARCH reply never sends it (types.rs:436-456): `with_data` = false skips the k
+  // device-to-host row copies.
+  std::vector<SearchResult> search_knn(const float* q, size_t n, size_t k, uint32_t ef = 0, bool with_data = false) const;
   // extension: nq independent queries in one device batch; result r of query i at [i][r]
   std::vector<std::vector<SearchResult>> search_knn_batch(const float* q, size_t nq, size_t n, size_t k, uint32_t ef = 0,
                                                            bool with_data = false) const;

@@ -23,6 +23,7 @@
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -594,6 +595,7 @@ int main(int argc, char** argv) {
       return 5;
     }
   }
+  const bool timing = std::getenv("FAKE_REDIS_TIMING") != nullptr;
   std::string line;
   while (std::getline(std::cin, line)) {
     std::istringstream ss(line);
@@ -613,7 +615,11 @@ int main(int argc, char** argv) {
         c.get_api = (void*)get_api;
         std::vector<RedisModuleString*> args;
         for (auto& t : w) args.push_back(new RedisModuleString{t});
+        const auto t0 = std::chrono::steady_clock::now();
         it->second.fn(&c, args.data(), (int)args.size());
+        if (timing)  // FAKE_REDIS_TIMING=1: wall time of the command handler alone (no script parsing, no reply printing)
+          std::fprintf(stderr, "T %s %.1f\n", it->first.c_str(),
+                       std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
         for (auto* a : args) delete a;
         for (auto* a : c.auto_strings) delete a;
         if (!c.have_root || !c.open.empty()) {
