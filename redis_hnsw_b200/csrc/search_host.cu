@@ -199,7 +199,8 @@ int Index::search_host_pipelined(uint64_t nq, const float* q, uint32_t k, uint32
       cudaError_t e = cudaStreamCreateWithFlags(&aux_stream[i], cudaStreamNonBlocking);
       if (e != cudaSuccess) return cuda_fail(e, "aux stream");
     }
-  const uint64_t n_chunks = std::min<uint64_t>(kCtlSlots, std::max<uint64_t>(2, nq / 16384));
+  // slot 0 belongs to the un-pipelined / device-pointer path (which may still be in flight on the caller's stream)
+  const uint64_t n_chunks = std::min<uint64_t>(kCtlSlots - 1, std::max<uint64_t>(2, nq / 16384));
   const uint64_t per = (nq + n_chunks - 1) / n_chunks;
   // size the control scratch before anything is in flight (ensure_scratch may reallocate)
   int rc = ensure_scratch(s_ctl, std::max<size_t>(64 + (size_t)nq * 4, 64 * kCtlSlots));
@@ -211,7 +212,7 @@ int Index::search_host_pipelined(uint64_t nq, const float* q, uint32_t k, uint32
     e = cudaMemcpyAsync((float*)d_q + lo * dim, q + lo * dim, n * dim * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_fail(e, "query H2D");
     if ((rc = search_device2(n, d_q + lo * dim, k, ef, efr, d_ids + lo * k, d_sims + lo * k, d_counts + lo, nullptr, st,
-                             (uint32_t)c)))
+                             (uint32_t)c + 1)))
       return rc;
     e = cudaMemcpyAsync(ids + lo * k, d_ids + lo * k, n * k * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(sims + lo * k, d_sims + lo * k, n * k * 4, cudaMemcpyDeviceToHost, st);
