@@ -96,3 +96,26 @@ def test_datasets_are_seeded():
     d = ((a[None, :, :] - qa[:, None, :]) ** 2).sum(-1)
     assert np.array_equal(np.sort(gt, 1), np.sort(np.argsort(d, 1)[:, :10], 1))
     assert data.recall_at_k(gt, gt) == 1.0
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/hnsw_b200.h must compile as C99 (no C++ or CUDA types in the signatures) and a C
+    program must link against the library."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "hnsw_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { hnsw_index_t* h = 0; int rc = hnsw_index_create(4, 5, 16, -1, &h);\n'
+                   '  printf("%d %s|%s\\n", rc, hnsw_version(), rc ? hnsw_last_error() : "");\n'
+                   '  if (h) { hnsw_index_destroy(h); }\n  return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "redis_hnsw_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lhnsw_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rc, rest = out.stdout.split(" ", 1)
+    assert rc in ("0", "5")            # 5 = HNSW_ERR_CUDA on a machine without a device: loud failure, no fallback
+    if rc == "5":
+        assert "CUDA" in rest or "device" in rest
