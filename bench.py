@@ -45,6 +45,24 @@ def log(*a):
         print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that banners written
+    by libraries (NCCL prints "NCCL version ..." on stdout at N > 1) cannot end up next to the line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -159,6 +177,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="name=value library option (tuning)")
     args = ap.parse_args()
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,7 +244,7 @@ def main():
                                  "sample": "%d queries per step, %d threads, oracle (C++ restatement of the reference; "
                                            "the Rust reference cannot be built here) on the same graph" % (sample, cores)},
                 "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -385,7 +404,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

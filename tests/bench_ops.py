@@ -6,7 +6,7 @@ querying operators on a big index, GPU vs the CPU oracle on the SAME graph.
   HNSW.NODE.ADD one node per call (hnsw_index_add, EXACT) and as one EXACT stream (hnsw_index_add_batch)
   HNSW.NODE.DEL one node per call (hnsw_index_delete)
 
-    python tools/bench_ops.py [--workload 1Mx128_M16_efc200] > gpurun_out/ops.json
+    python tests/bench_ops.py [--workload 1Mx128_M16_efc200] > gpurun_out/ops.json
 """
 import argparse
 import json
