@@ -63,11 +63,41 @@ SYMBOLS = {
 _lib = None
 
 
-def build(jobs=8):
-    """Compile libhnsw_b200.so for sm_100a with the in-tree Makefile (nvcc cross-compiles without a GPU)."""
+def _source_hash():
+    """sha256 over everything the two libraries are compiled from (sources, headers, Makefiles)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    roots = [os.path.join(_HERE, "csrc"), os.path.join(os.path.dirname(_HERE), "include"),
+             os.path.join(os.path.dirname(_HERE), "tests", "fake_redis")]
+    for root in roots:
+        for d, _, files in sorted(os.walk(root)):
+            for f in sorted(files):
+                if f.endswith((".cu", ".cuh", ".hpp", ".cpp", ".h", "Makefile")):
+                    h.update(f.encode())
+                    with open(os.path.join(d, f), "rb") as fh:
+                        h.update(fh.read())
+    return h.hexdigest()
+
+
+def build(jobs=8, force=False):
+    """Compile libhnsw_b200.so for sm_100a with the in-tree Makefile (nvcc cross-compiles without a GPU).
+
+    The built libraries travel to the GPU box next to a stamp holding the hash of the sources they were made from; when
+    the stamp matches, nothing is recompiled (file times do not survive every copy, and the object files under build/ do
+    not travel)."""
+    stamp = SO_PATH + ".stamp"
+    want = _source_hash()
+    host = os.path.join(os.path.dirname(_HERE), "tests", "fake_redis", "fake_redis_host")
+    if not force and all(os.path.exists(p) for p in (SO_PATH, REDIS_MODULE_PATH, host, stamp)):
+        with open(stamp) as fh:
+            if fh.read().strip() == want:
+                return SO_PATH
     subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j%d" % jobs], stdout=subprocess.DEVNULL)
     # the Redis module (host side, plain C++ over the C ABI) and the fake module host the tests drive it with
     subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc", "redis")], stdout=subprocess.DEVNULL)
+    with open(stamp, "w") as fh:
+        fh.write(want + "\n")
     return SO_PATH
 
 
