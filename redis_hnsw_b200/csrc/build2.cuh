@@ -27,17 +27,7 @@ __global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) build_
   const int warp = threadIdx.x >> 5;
   unsigned char* base = smem2 + (size_t)warp * warp2_smem_bytes(32 * C, S, a.vis_slots, sizeof(T));
   Warp2<C, S, T> w;
-  w.stage = reinterpret_cast<const float4*>(base);
-  w.stage_s = smem_u32(base);
-  const uint32_t tab_bytes = (a.vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
-  w.seen.tab = reinterpret_cast<T*>(base + (size_t)S * C * 128);
-  w.seen.n16 = tab_bytes / 16;
-  w.seen.bits = 31 - __clz(a.vis_slots);
-  w.ids = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128 + tab_bytes);
-  w.bar = smem_u32(w.ids + 32);
-  w.parity = 0;
-  if (lane == 0) mbar_init(w.bar, 1);
-  __syncwarp();
+  warp2_setup<C, S, T>(w, base, a.vis_slots, lane);
 
   CandList<EFR> L;
   Counters cnt = {0, 0, 0};
@@ -164,22 +154,6 @@ __device__ __forceinline__ void reprune_select2(const Graph& g, Warp2<C, S, T>& 
     }
   }
   if (np) flush(np);
-}
-
-template <int C, int S, class T>
-__device__ __forceinline__ unsigned char* warp2_setup(Warp2<C, S, T>& w, unsigned char* base, uint32_t vis_slots, int lane) {
-  w.stage = reinterpret_cast<const float4*>(base);
-  w.stage_s = smem_u32(base);
-  const uint32_t tab_bytes = (vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
-  w.seen.tab = reinterpret_cast<T*>(base + (size_t)S * C * 128);
-  w.seen.n16 = tab_bytes / 16;
-  w.seen.bits = 31 - __clz(vis_slots);
-  w.ids = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128 + tab_bytes);
-  w.bar = smem_u32(w.ids + 32);
-  w.parity = 0;
-  if (lane == 0) mbar_init(w.bar, 1);
-  __syncwarp();
-  return base + warp2_smem_bytes(32 * C, S, vis_slots, sizeof(T));
 }
 
 // update_node_connections (core.rs:776-822) for node `e` whose re-selected list is in L; shared by insert and delete.

@@ -59,6 +59,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS), skipped when `on` is false; completion with cp_async_wait_all
+__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, bool on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %2, 0;\n"
+      "@p cp.async.cg.shared.global [%0], [%1], 16;\n"
+      "}\n" ::"r"(dst),
+      "l"(src), "r"((int)on)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------- transposed hsum of S row partials
@@ -180,29 +193,68 @@ __device__ __forceinline__ float staged_partial(const float (&q)[C], const float
 
 // Evaluate the ids flagged new (lane j holds nb) and apply them to the list in lane order (= adjacency-list order,
 // core.rs:646-667).  `adj_prefetch` = base of the level-0 adjacency rows (or null) for the L2 prefetch of admitted ids.
-template <int EFR, int C, int S, class T>
+// rows per unconditional group of eval_and_admit: about 32 floats of row data per lane, a power of two, 1 <= G <= min(S, 8)
+__host__ __device__ constexpr int partial_group(int C, int S) {
+  int g = 1;
+  while (g * 2 * C <= 32 && g * 2 <= S && g * 2 <= 8) g *= 2;
+  return g;
+}
+
+// COPY selects how the rows of a round reach the stage:
+//   0  one bulk-async copy per row (UBLKCP) completing on the warp's mbarrier.  Bulk copies are warp-uniform
+//      instructions, so a warp issues its rows one after the other (~9 instructions per row).
+//   1  (V == 4 layouts, rows of <= 1 KB) one 16-byte cp.async per lane and 512-byte group (LDGSTS.128): a row is one
+//      warp-wide instruction, the ids come from the compacted list in shared memory; completion = cp.async.wait_all.
+template <int EFR, int C, int S, class T, int COPY = 0>
 __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w, uint32_t nb, uint32_t newmask, int ef,
                                                CandList<EFR>& L, const uint32_t* adj_prefetch, int lane) {
   constexpr uint32_t RB = Warp2<C, S, T>::kRowBytes;
+  static_assert(COPY == 0 || (C % 4 == 0), "the cp.async path needs the 4-wide lane-permuted layout");
   const int n_new = __popc(newmask);
   const int rank = __popc(newmask & ((1u << lane) - 1u));
   const bool mine_new = (newmask >> lane) & 1u;
   for (int base = 0; base < n_new; base += S) {
     const int nr = min(S, n_new - base);
     __syncwarp();  // the previous round's reads of the stage and of ids[] are complete
-    if (lane == 0) mbar_expect_tx(w.bar, (uint32_t)nr * RB);
-    __syncwarp();
-    if (mine_new && rank >= base && rank < base + nr) {
-      w.ids[rank - base] = nb;
-      bulk_g2s(w.stage_s + (uint32_t)(rank - base) * RB, g.vecs + (size_t)nb * (32 * C), RB, w.bar);
+    if constexpr (COPY == 0) {
+      if (lane == 0) mbar_expect_tx(w.bar, (uint32_t)nr * RB);
+      __syncwarp();
+      if (mine_new && rank >= base && rank < base + nr) {
+        w.ids[rank - base] = nb;
+        bulk_g2s(w.stage_s + (uint32_t)(rank - base) * RB, g.vecs + (size_t)nb * (32 * C), RB, w.bar);
+      }
+      mbar_wait(w.bar, w.parity);
+      w.parity ^= 1u;
+    } else {
+      if (mine_new && rank >= base && rank < base + nr) w.ids[rank - base] = nb;
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        const uint32_t rid = w.ids[r];                     // broadcast read; stale beyond nr (copy predicated off)
+        const float* src = g.vecs + (size_t)rid * (32 * C) + lane * 4;
+#pragma unroll
+        for (int q4 = 0; q4 < C / 4; ++q4)
+          cp_async16_if(w.stage_s + (uint32_t)r * RB + (uint32_t)q4 * 512u + (uint32_t)lane * 16u, src + q4 * 128, r < nr);
+      }
+      cp_async_wait_all();
     }
-    mbar_wait(w.bar, w.parity);
-    w.parity ^= 1u;
     __syncwarp();
+    // Partials are formed for whole groups of G rows without looking at nr: the loads of a group issue back to back
+    // and its arithmetic interleaves (a per-row test costs 5 instructions and serialises the shared-memory latencies).
+    // Rows at or beyond nr hold older rows (zeros before the first use); their sums are never looked at.
+    constexpr int G = partial_group(C, S);
     float acc[S];
     const float* st = reinterpret_cast<const float*>(w.stage);
 #pragma unroll
-    for (int r = 0; r < S; ++r) acc[r] = (r < nr) ? staged_partial<C>(w.q, st + (size_t)r * (32 * C), lane) : 0.0f;
+    for (int g0 = 0; g0 < S; g0 += G) {
+      if (g0 == 0 || g0 < nr) {
+#pragma unroll
+        for (int r = g0; r < g0 + G; ++r) acc[r] = staged_partial<C>(w.q, st + (size_t)r * (32 * C), lane);
+      } else {
+#pragma unroll
+        for (int r = g0; r < g0 + G; ++r) acc[r] = 0.0f;
+      }
+    }
     const float s = reduce_rows<S>(acc, lane);
     const uint32_t id = (lane < nr) ? w.ids[lane] : kEmpty;
     uint32_t cand = __ballot_sync(kFull, lane < nr && L.admits(s, ef));
@@ -219,7 +271,7 @@ __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w
   }
 }
 
-template <int EFR, int C, int S, class T>
+template <int EFR, int C, int S, class T, int COPY = 0>
 __device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S, T>& w, uint32_t nb, int ef, CandList<EFR>& L,
                                               Counters& cnt, const uint32_t* adj_prefetch, int lane) {
   const bool valid = nb != kEmpty;
@@ -230,11 +282,11 @@ __device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S, T>& w,
   const uint32_t newmask = __ballot_sync(kFull, is_new);
   if (!newmask) return;
   cnt.n_dist += __popc(newmask);                                 // core.rs:652-656
-  eval_and_admit<EFR, C, S, T>(g, w, nb, newmask, ef, L, adj_prefetch, lane);
+  eval_and_admit<EFR, C, S, T, COPY>(g, w, nb, newmask, ef, L, adj_prefetch, lane);
 }
 
 // core.rs:607-675
-template <int EFR, int C, int S, class T>
+template <int EFR, int C, int S, class T, int COPY = 0>
 __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w, uint32_t ep, int ef, uint32_t level,
                                               CandList<EFR>& L, Counters& cnt, int lane) {
   w.seen.clear(lane);
@@ -244,7 +296,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
     const uint32_t nb = lane == 0 ? ep : kEmpty;                 // core.rs:617-628
     if (lane == 0) w.seen.test_and_set(ep);
     cnt.n_dist += 1;
-    eval_and_admit<EFR, C, S, T>(g, w, nb, 1u, ef, L, adj_prefetch, lane);
+    eval_and_admit<EFR, C, S, T, COPY>(g, w, nb, 1u, ef, L, adj_prefetch, lane);
   }
   for (;;) {
     const int pos = L.first_unexpanded();                        // core.rs:631-638
@@ -260,7 +312,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
     for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
       const uint32_t nb = row[c * 32 + lane];
       more = __shfl_sync(kFull, nb, 31) != kEmpty;               // rows are compact: an empty tail ends the list
-      expand_chunk2<EFR, C, S, T>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
+      expand_chunk2<EFR, C, S, T, COPY>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
     }
     if (more) {                                                  // overflow rows (degree is unbounded); rare
       uint32_t link = *ovf;
@@ -268,7 +320,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
         uint32_t nb = g.pool[(size_t)link * 32 + lane];
         link = __shfl_sync(kFull, nb, 31);
         if (lane == 31) nb = kEmpty;
-        expand_chunk2<EFR, C, S, T>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
+        expand_chunk2<EFR, C, S, T, COPY>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
       }
     }
   }
@@ -277,6 +329,25 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
 // shared memory per warp (bytes), 128-byte aligned pieces: stage | visited | ids | mbarrier
 __host__ __device__ inline size_t warp2_smem_bytes(uint32_t dim, int S, uint32_t vis_slots, uint32_t slot_bytes) {
   return (size_t)S * dim * 4 + (((size_t)vis_slots * slot_bytes + 127) & ~(size_t)127) + 128 + 128;
+}
+
+template <int C, int S, class T>
+__device__ __forceinline__ unsigned char* warp2_setup(Warp2<C, S, T>& w, unsigned char* base, uint32_t vis_slots, int lane) {
+  w.stage = reinterpret_cast<const float4*>(base);
+  w.stage_s = smem_u32(base);
+  const uint32_t tab_bytes = (vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
+  w.seen.tab = reinterpret_cast<T*>(base + (size_t)S * C * 128);
+  w.seen.n16 = tab_bytes / 16;
+  w.seen.bits = 31 - __clz(vis_slots);
+  w.ids = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128 + tab_bytes);
+  w.bar = smem_u32(w.ids + 32);
+  w.parity = 0;
+  if (lane == 0) mbar_init(w.bar, 1);
+  // the stage starts as zeros: eval_and_admit forms partials for whole row groups, also beyond the rows of a round
+  uint4* z = reinterpret_cast<uint4*>(base);
+  for (uint32_t i = lane; i < (uint32_t)S * C * 8; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  return base + warp2_smem_bytes(32 * C, S, vis_slots, sizeof(T));
 }
 
 // core.rs:477-486, 865-892
@@ -290,24 +361,14 @@ struct Search2Bounds {
   static constexpr int kMinBlocks = C > 8 ? 4 : (EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6));
 };
 
-template <int EFR, int C, int S, class T>
+template <int EFR, int C, int S, class T, int COPY = 0>
 __global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) search_knn2_kernel(Graph g, SearchArgs a) {
   extern __shared__ __align__(128) unsigned char smem2[];
   const int lane = lane_id();
   const int warp = threadIdx.x >> 5;
   unsigned char* base = smem2 + (size_t)warp * warp2_smem_bytes(32 * C, S, a.vis_slots, sizeof(T));
   Warp2<C, S, T> w;
-  w.stage = reinterpret_cast<const float4*>(base);
-  w.stage_s = smem_u32(base);
-  const uint32_t tab_bytes = (a.vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
-  w.seen.tab = reinterpret_cast<T*>(base + (size_t)S * C * 128);
-  w.seen.n16 = tab_bytes / 16;
-  w.seen.bits = 31 - __clz(a.vis_slots);
-  w.ids = reinterpret_cast<uint32_t*>(base + (size_t)S * C * 128 + tab_bytes);
-  w.bar = smem_u32(w.ids + 32);
-  w.parity = 0;
-  if (lane == 0) mbar_init(w.bar, 1);
-  __syncwarp();
+  warp2_setup<C, S, T>(w, base, a.vis_slots, lane);
 
   CandList<EFR> L;
   uint32_t evals = 0;
@@ -325,7 +386,7 @@ __global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) search
     if (entry >= 0) {                                            // core.rs:481-483
       uint32_t ep = (uint32_t)entry;
       for (int lc = g.meta[kMetaMaxLayer]; lc >= 0; --lc) {      // core.rs:869-876
-        search_layer2<EFR, C, S, T>(g, w, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, cnt, lane);
+        search_layer2<EFR, C, S, T, COPY>(g, w, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, cnt, lane);
         float s;
         if (lc > 0) L.get(0, lane, false, ep, s);
       }

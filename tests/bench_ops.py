@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--n-del", type=int, default=300)
     ap.add_argument("--cpu-add", type=int, default=200)
     ap.add_argument("--cpu-del", type=int, default=100)
+    ap.add_argument("--only", default="all", choices=["all", "search"])
     args = ap.parse_args()
     import oracle
     import redis_hnsw_b200 as r
@@ -57,30 +58,51 @@ def main():
     orc.import_graph(x, dev.export_graph())
 
     # ---- HNSW.SEARCH, one query per call
-    for i in range(20):
-        dev.search(q[i], 10, ef=args.ef)
-    lat = []
-    for i in range(args.n_search):
-        t = time.perf_counter()
-        ids, sims = dev.search(q[i], 10, ef=args.ef)
-        lat.append(time.perf_counter() - t)
-    lat32 = []
-    dev.set_option("stage_rows", 32)   # latency mode: the whole adjacency chunk of a hop in one staging round
-    for i in range(20):
-        dev.search(q[i], 10, ef=args.ef)
-    for i in range(args.n_search):
-        t = time.perf_counter()
-        dev.search(q[i], 10, ef=args.ef)
-        lat32.append(time.perf_counter() - t)
-    dev.set_option("stage_rows", 0)
-    clat = []
+    def single(n_calls):
+        for i in range(20):
+            dev.search(q[i], 10, ef=args.ef)
+        lat, res = [], []
+        for i in range(n_calls):
+            t = time.perf_counter()
+            ids, sims = dev.search(q[i], 10, ef=args.ef)
+            lat.append(time.perf_counter() - t)
+            res.append(ids)
+        return lat, res
+
+    lat, res = single(args.n_search)
+    dev.set_option("row_copy", 1)                    # cp.async row copies instead of bulk-async ones (search2.cuh, COPY)
+    lat_nospec, res_nospec = single(args.n_search)
+    dev.set_option("row_copy", 0)
+    clat, cres = [], []
     for i in range(args.n_search):
         t = time.perf_counter()
         oids, osims = orc.search(q[i], 10, ef=args.ef)
         clat.append(time.perf_counter() - t)
-    out["search_single"] = {"gpu_us_p50": pct(lat, 50), "gpu_us_p99": pct(lat, 99), "gpu_stage32_us_p50": pct(lat32, 50), "cpu_oracle_us_p50": pct(clat, 50),
-                            "cpu_oracle_us_p99": pct(clat, 99), "n": args.n_search,
+        cres.append(oids)
+    same_spec = all(np.array_equal(a, b) for a, b in zip(res, res_nospec))
+    same_orc = float(np.mean([np.array_equal(a, b) for a, b in zip(res, cres)]))
+    out["search_single"] = {"gpu_us_p50": pct(lat, 50), "gpu_us_p99": pct(lat, 99), "gpu_row_copy1_us_p50": pct(lat_nospec, 50),
+                            "cpu_oracle_us_p50": pct(clat, 50), "cpu_oracle_us_p99": pct(clat, 99), "n": args.n_search,
+                            "ids_equal_both_row_copy_modes": bool(same_spec), "ids_equal_oracle_fraction": same_orc,
                             "note": "python ctypes call overhead (~5 us) included on both sides"}
+    # ---- small batches through hnsw_index_search_batch (host buffers): latency of one call and the rate it gives
+    sweep = {}
+    for nb in (1, 8, 32, 148, 1250, 10000):
+        if nb > args.n_search:
+            break
+        qb = np.ascontiguousarray(q[:nb])
+        for _ in range(3):
+            dev.search_batch(qb, 10, ef=args.ef)
+        ts = []
+        for _ in range(30):
+            t = time.perf_counter()
+            dev.search_batch(qb, 10, ef=args.ef)
+            ts.append(time.perf_counter() - t)
+        sweep[nb] = {"call_us_p50": pct(ts, 50), "qps": nb / float(np.median(ts))}
+    out["search_batch_sweep"] = sweep
+    if args.only == "search":
+        print(json.dumps(out), flush=True)
+        return
 
     # ---- HNSW.NODE.ADD: CPU oracle first (on its own copy of the graph), then the device, same vectors and levels
     t = time.perf_counter()

@@ -34,8 +34,10 @@ def test_staged_kernel_counters_and_options(name):
     q = c["q"][:300]
     oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=64)
     ok = ost[:, 3] == 0
-    for rows, slots, tag in ((0, 0, 0), (4, 64, 0), (8, 64, 32), (16, 256, 0), (32, 4096, 32)):
+    for rows, slots, tag, copy in ((0, 0, 0, 0), (4, 64, 0, 0), (8, 64, 32, 0), (16, 256, 0, 0), (32, 4096, 32, 0),
+                                   (0, 0, 0, 1), (8, 64, 32, 1), (32, 256, 0, 1)):
         dev.set_option("search_impl", 2)
+        dev.set_option("row_copy", copy)      # 1: cp.async row copies instead of bulk-async ones (128-d rows only)
         dev.set_option("stage_rows", rows)
         dev.set_option("recent_slots", slots)
         dev.set_option("recent_tag", tag)
@@ -47,6 +49,32 @@ def test_staged_kernel_counters_and_options(name):
         assert np.all(st[ok, 0] >= ost[ok, 0])
         if slots == 0:
             assert st[ok, 0].sum() <= 1.5 * ost[ok, 0].sum()
+
+
+@pytest.mark.parametrize("name,efs", [("cfg1_10k_d32_m5", (1, 16, 100)), ("d128_m16", (8, 64, 200, 512)), ("d768_m32", (16, 128))])
+def test_latency_mode_parity(name, efs):
+    """Calls with fewer queries than SMs take a 32-row stage (one staging round per adjacency chunk); both row-copy
+    flavours: ids, sims, counts, hops and adjacency counters equal the oracle's."""
+    c = case(name)
+    dev = device_index(name)
+    for ef in efs:
+        for lo, n in ((0, 1), (1, 7), (8, 100)):
+            q = c["q"][lo:lo + n]
+            oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=ef)
+            ok = ost[:, 3] == 0
+            for copy in (0, 1):
+                dev.set_option("row_copy", copy)
+                ids, sims, counts = dev.search_batch(q, 10, ef=ef)
+                assert np.array_equal(counts, ocounts)
+                assert np.array_equal(ids[ok], oids[ok])
+                assert np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
+                dev.set_option("search_impl", 2)      # same kernel, counters requested
+                ids, sims, counts, st = dev.search_batch(q, 10, ef=ef, stats=True)
+                dev.set_option("search_impl", 0)
+                assert np.array_equal(ids[ok], oids[ok]) and np.array_equal(counts, ocounts)
+                assert np.array_equal(st[ok, 1:3].astype(np.uint64), ost[ok, 1:3])
+                assert np.all(st[ok, 0] >= ost[ok, 0])
+    dev.set_option("row_copy", 0)
 
 
 def test_default_ef_is_ef_construction():
