@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) build_
     uint32_t ep = entry;
     for (int lc = l_max; lc >= 0; --lc) {
       const bool link = lc <= l;
-      search_layer2<EFR, C, S, T>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane);  // core.rs:513, :524
+      search_layer2<EFR, C, S, T, RowCopy<C>::kDefault>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane);  // core.rs:513, :524
       float s;
       L.get(0, lane, false, ep, s);                                                              // core.rs:514, :576
       if (!link) continue;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void reprune_select2(const Graph& g, Warp2<C, S, T>& 
     const uint32_t rest = lane + 32 < (int)np ? pend[lane + 32] : kEmpty;
     __syncwarp();
     cnt.n_dist += n;
-    eval_and_admit<EFR, C, S, T>(g, w, nb, n >= 32 ? kFull : ((1u << n) - 1u), cap, L, nullptr, lane);
+    eval_and_admit<EFR, C, S, T, RowCopy<C>::kDefault>(g, w, nb, n >= 32 ? kFull : ((1u << n) - 1u), cap, L, nullptr, lane);
     if (lane + 32 < (int)np) pend[lane] = rest;
     np -= n;
     __syncwarp();
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a)
       const bool link = lc <= l;
       const uint32_t cap = lc == 0 ? a.cap0 : a.capU;             // core.rs:560
       load_q_from_slab<C, S, T>(w, g, q, lane);
-      search_layer2<EFR, C, S, T>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane);   // :513, :524
+      search_layer2<EFR, C, S, T, RowCopy<C>::kDefault>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane);   // :513, :524
       float s;
       L.get(0, lane, false, ep, s);                               // :514 / :576
       if (!link) continue;

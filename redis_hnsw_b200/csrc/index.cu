@@ -642,7 +642,7 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
     if (value != 0 && value != 32) return fail(HNSW_ERR_INVALID, "recent_tag must be 0 (auto) or 32");
     ix.opt_recent_tag = (int)value;
   } else if (n == "row_copy") {
-    if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "row_copy must be 0 (bulk-async copies) or 1 (cp.async, 128-d rows)");
+    if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "row_copy must be 0 (bulk-async copies everywhere) or 1 (cp.async for 32-d / 128-d rows)");
     ix.opt_row_copy = (int)value;
   } else if (n == "build_batch") {
     if (value < 1) return fail(HNSW_ERR_INVALID, "build_batch must be >= 1");

@@ -40,7 +40,7 @@ enum KernelId : int {
   kKernSearch2 = 16,
 };
 // build_search2_kernel (TMA-staged K1 of the batched builder): id = kKernBuildSearch2 + (16-bit visited tags ? 1 : 0)
-constexpr int kKernSearch2Cp = 24;  // search_knn2_kernel with cp.async row copies (C == 4 only): + 2 * (S == 32) + (16-bit tags ? 1 : 0); S = 8 or 32
+constexpr int kKernSearch2Cp = 24;  // search_knn2_kernel with cp.async row copies (RowCopy<C>::kOk): + 2 * log2(S / 4) + (16-bit tags ? 1 : 0)
 constexpr int kKernBuildSearch2 = 32;
 constexpr int kKernExact2 = 40;   // insert_exact2_kernel / delete_exact2_kernel (TMA-staged, build2.cuh)
 constexpr int kKernDelete2 = 41;
@@ -109,10 +109,14 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
       case kKernSearch2 + 5: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint16_t>), SearchArgs)
       case kKernSearch2 + 6: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint32_t>), SearchArgs)
       case kKernSearch2 + 7: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t>), SearchArgs)
-      case kKernSearch2Cp + 0: if constexpr (Dist::C == 4) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, uint32_t, 1>), SearchArgs) break;
-      case kKernSearch2Cp + 1: if constexpr (Dist::C == 4) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, uint16_t, 1>), SearchArgs) break;
-      case kKernSearch2Cp + 2: if constexpr (Dist::C == 4) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint32_t, 1>), SearchArgs) break;
-      case kKernSearch2Cp + 3: if constexpr (Dist::C == 4) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 0: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, uint32_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 1: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, uint16_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 2: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, uint32_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 3: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, uint16_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 4: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint32_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 5: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint16_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 6: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint32_t, 1>), SearchArgs) break;
+      case kKernSearch2Cp + 7: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t, 1>), SearchArgs) break;
       case kKernBuildSearch2 + 0: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
       case kKernBuildSearch2 + 1: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint16_t>), FastArgs)
       case kKernBuildReprune2 + 0: HNSW_RUN((build_reprune2_kernel<EFR, Dist::C, uint32_t>), FastArgs)

@@ -59,16 +59,29 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-// 16-byte asynchronous copy global -> shared (LDGSTS), skipped when `on` is false; completion with cp_async_wait_all
-__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, bool on) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %2, 0;\n"
-      "@p cp.async.cg.shared.global [%0], [%1], 16;\n"
-      "}\n" ::"r"(dst),
-      "l"(src), "r"((int)on)
-      : "memory");
+// BYTES-wide (4 / 8 / 16) asynchronous copy global -> shared (LDGSTS), skipped when `on` is false; completion with
+// cp_async_wait_all
+template <int BYTES>
+__device__ __forceinline__ void cp_async_if(uint32_t dst, const void* src, bool on) {
+  if constexpr (BYTES == 16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n"
+        "}\n" ::"r"(dst),
+        "l"(src), "r"((int)on)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "@p cp.async.ca.shared.global [%0], [%1], %3;\n"
+        "}\n" ::"r"(dst),
+        "l"(src), "r"((int)on), "n"(BYTES)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -202,14 +215,22 @@ __host__ __device__ constexpr int partial_group(int C, int S) {
 
 // COPY selects how the rows of a round reach the stage:
 //   0  one bulk-async copy per row (UBLKCP) completing on the warp's mbarrier.  Bulk copies are warp-uniform
-//      instructions, so a warp issues its rows one after the other (~9 instructions per row).
-//   1  (V == 4 layouts, rows of <= 1 KB) one 16-byte cp.async per lane and 512-byte group (LDGSTS.128): a row is one
+//      instructions, so a warp issues its rows one after the other (~9 instructions per row: ELECT, 4 x R2UR, ...).
+//   1  one cp.async per lane and lane-permuted group of the row (LDGSTS, 4 * V bytes per lane): a 128-d row is ONE
 //      warp-wide instruction, the ids come from the compacted list in shared memory; completion = cp.async.wait_all.
+//      Measured at 1M x 128, ef 64: 9.29 -> 9.81 M QPS (profiles/r1e_search.md).  The default where a row is at most two
+//      instructions (RowCopy<C>); 768-d rows (6 per row) stay on bulk copies.
+template <int C>
+struct RowCopy {
+  static constexpr int kGroups = C / RowRegs<C>::V;       // cp.async instructions per row
+  static constexpr bool kOk = kGroups <= 2;
+  static constexpr int kDefault = kOk ? 1 : 0;
+};
+
 template <int EFR, int C, int S, class T, int COPY = 0>
 __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w, uint32_t nb, uint32_t newmask, int ef,
                                                CandList<EFR>& L, const uint32_t* adj_prefetch, int lane) {
   constexpr uint32_t RB = Warp2<C, S, T>::kRowBytes;
-  static_assert(COPY == 0 || (C % 4 == 0), "the cp.async path needs the 4-wide lane-permuted layout");
   const int n_new = __popc(newmask);
   const int rank = __popc(newmask & ((1u << lane) - 1u));
   const bool mine_new = (newmask >> lane) & 1u;
@@ -231,10 +252,12 @@ __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w
 #pragma unroll
       for (int r = 0; r < S; ++r) {
         const uint32_t rid = w.ids[r];                     // broadcast read; stale beyond nr (copy predicated off)
-        const float* src = g.vecs + (size_t)rid * (32 * C) + lane * 4;
+        constexpr int V = RowRegs<C>::V;                   // a group = 32 lanes x V floats, lane t's slice at float t * V
+        const float* src = g.vecs + (size_t)rid * (32 * C) + lane * V;
 #pragma unroll
-        for (int q4 = 0; q4 < C / 4; ++q4)
-          cp_async16_if(w.stage_s + (uint32_t)r * RB + (uint32_t)q4 * 512u + (uint32_t)lane * 16u, src + q4 * 128, r < nr);
+        for (int q = 0; q < C / V; ++q)
+          cp_async_if<4 * V>(w.stage_s + (uint32_t)r * RB + (uint32_t)(q * 128 * V) + (uint32_t)(lane * 4 * V), src + q * 32 * V,
+                             r < nr);
       }
       cp_async_wait_all();
     }

@@ -160,8 +160,9 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   const int warps = block / 32;
   const size_t smem = (size_t)warps * per_warp;
   if (smem > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the staged search kernel");
-  const bool cp = opt_row_copy == 1 && kind == kKindR4 && (S == 8 || S == 32);
-  const int id = cp ? kKernSearch2Cp + (S == 32 ? 2 : 0) + (tag16 ? 1 : 0) : search2_id(S, tag16);
+  // rows of up to two cp.async instructions (32-d, 128-d) are copied with cp.async, longer ones with bulk-async copies
+  const bool cp = opt_row_copy == 1 && (kind == kKindR4 || kind == kKindR1);
+  const int id = search2_id(S, tag16) + (cp ? kKernSearch2Cp - kKernSearch2 : 0);
   int occ = occupancy(kind, id, efr, block, smem);
   if (occ < 1) return fail(HNSW_ERR_CUDA, "staged search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
