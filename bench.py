@@ -173,7 +173,8 @@ def main():
     ap.add_argument("--nq", type=int, default=100_000, help="queries per GPU per step")
     ap.add_argument("--ef", type=int, default=0, help="0 = smallest ef of the sweep with recall@10 >= 0.95")
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--cpu-sample", type=int, default=10_000)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="queries of the CPU legs; 0 = sized for 10-30 s of CPU work (40 000 at 128-d / ef 64, scaled by row size and ef)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="name=value library option (tuning)")
     args = ap.parse_args()
@@ -216,6 +217,8 @@ def main():
         dist.broadcast(t, 0)
         ef = int(t.item())
     recall = curve.get(ef)
+    if not args.cpu_sample:
+        args.cpu_sample = max(500, int(40_000 * (128.0 / dim) * (64.0 / max(ef, 16))))
 
     base_cfg = {"workload": wl, "n": n, "dim": dim, "M": m, "ef_construction": efc, "ef_search": ef, "k": args.k,
                 "queries_per_gpu_per_step": nq, "dataset": "lowrank r=%d sigma=0.05 seed=123" % r_lat if ds == "lowrank" else "uniform seed=123",
@@ -366,6 +369,9 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": alg_bytes,
+                # DRAM bytes actually moved (ncu) over the same launch time: L2 serves part of the algorithmic bytes, so
+                # `frac` can exceed 1 while DRAM itself stays below its peak
+                "traffic_frac": (traffic / (kernel_ms / 1e3) / 1e9 / peak) if traffic else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel": "search_knn2_kernel (one launch per step; duration = CUDA events around the step on the launch stream)",

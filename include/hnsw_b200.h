@@ -183,7 +183,8 @@ int hnsw_index_adopt_replica(hnsw_index_t* idx);
 
 /* Named integer options: "visited_slots" (per-query visited hash slots, power of two, 0 = auto),
  * "search_ctas_per_sm", "build_batch" (nodes per batch of the FAST builder), "build_impl" (0 auto, 1 = register-staged
- * batch searches, 2 = TMA-staged), "search_impl", "stage_rows", "recent_slots", "recent_tag", "block".
+ * batch searches, 2 = TMA-staged), "search_impl", "stage_rows", "recent_slots", "recent_tag", "search_block", "row_copy"
+ * (1 = cp.async row staging for 32-d / 128-d rows, the default; 0 = bulk-async copies for every dimension).
  * Unknown names -> HNSW_ERR_INVALID. */
 int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
