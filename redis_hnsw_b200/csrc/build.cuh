@@ -7,6 +7,8 @@
 //     When the search stops every member of W has been expanded, so every node of N(W) was evaluated by the
 //     search itself and either sits in W or lost against W's worst.  Hence top-m(W ∪ N(W)) == the first
 //     min(m, |W|) entries of W: the reference's 2-hop sweep at this call site is redundant work and is skipped.
+//     The one exception is ef_construction < m with W full (|W| = ef_construction < m): nodes turned away only because
+//     W was full can still be selected, so there the sweep IS computed (EXACT kernels; FAST builds run EXACT then).
 //   * connect: q.list = R nearest-first; q appended to the tail of every r in R              (core.rs:532, 759-774)
 //   * shrink: for e in R nearest-first, if |N(e)| > cap (m_max_0 on level 0, m_max above):   (core.rs:540-574)
 //       E' = top-cap by sim(e, .) over N(e) ∪ N(N(e)) \ {e}   -- a real 2-hop distance sweep (core.rs:568)
@@ -392,6 +394,19 @@ __global__ void __launch_bounds__(32) insert_exact_kernel(Graph g, ExactArgs a) 
       L.get(0, lane, false, ep, s);                             // :514 / :576 nearest of w
       if (!link) continue;
       // select_neighbors(q, w, m) == first min(m, |w|) entries of w (see the header of this file)    core.rs:531
+      // ... unless ef_construction < m and w came back full: then N(w) can hold nodes the search turned away only
+      // because w was full, and the reference's sweep (core.rs:698-721) picks them up until m are selected.
+      if (a.efc < a.m && (uint32_t)L.len == a.efc) {
+        const uint32_t n_w = (uint32_t)L.len;
+#pragma unroll
+        for (int r = 0; r < EFR; ++r) {
+          uint32_t e = r * 32 + lane;
+          if (e < n_w) old[e] = L.id[r] & ~kExpanded;
+        }
+        __syncwarp();
+        ok = reprune_select<EFR, Dist>(g, dist, q, (uint32_t)lc, (int)a.m, old, n_w, L, vis, cnt, lane);  // dist holds q
+        if (!ok) break;
+      }
       const uint32_t n_sel = min((uint32_t)L.len, a.m);
 #pragma unroll
       for (int r = 0; r < EFR; ++r) {

@@ -225,11 +225,31 @@ __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a)
       float s;
       L.get(0, lane, false, ep, s);                               // :514 / :576
       if (!link) continue;
-      const uint32_t n_sel = min((uint32_t)L.len, a.m);           // core.rs:531 (build.cuh header)
+      uint32_t n_sel = min((uint32_t)L.len, a.m);                 // core.rs:531 (build.cuh header)
+      if (a.efc < a.m && (uint32_t)L.len == a.efc) {
+        // ef_construction < m and w came back full: N(w) can hold nodes the search turned away only because w was
+        // full, and the reference's sweep (core.rs:698-721) picks them up until m are selected.  Same set computation
+        // as a re-selection: top-m by sim(q, .) over w U N(w) \ {q}; w.q still holds q's vector.
+        const uint32_t n_w = (uint32_t)L.len;
 #pragma unroll
-      for (int r = 0; r < EFR; ++r) {
-        uint32_t e = r * 32 + lane;
-        if (e < n_sel) sel[e] = L.id[r] & ~kExpanded;
+        for (int r = 0; r < EFR; ++r) {
+          uint32_t e = r * 32 + lane;
+          if (e < n_w) old[e] = L.id[r] & ~kExpanded;
+        }
+        __syncwarp();
+        reprune_select2<ER, C, S, T>(g, w, q, (uint32_t)lc, (int)a.m, old, n_w, R, cnt, lane, kEmpty, keep_add);
+        n_sel = min((uint32_t)R.len, a.m);
+#pragma unroll
+        for (int r = 0; r < ER; ++r) {
+          uint32_t e = r * 32 + lane;
+          if (e < n_sel) sel[e] = R.id[r] & ~kExpanded;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < EFR; ++r) {
+          uint32_t e = r * 32 + lane;
+          if (e < n_sel) sel[e] = L.id[r] & ~kExpanded;
+        }
       }
       __syncwarp();
       {                                                           // connect_neighbors (core.rs:759-774)

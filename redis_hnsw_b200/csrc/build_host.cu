@@ -549,7 +549,9 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
     start = 1;
   }
   const uint32_t rest = (uint32_t)count - start;
-  if (mode == HNSW_BUILD_EXACT) {
+  // ef_construction < m: select_neighbors at core.rs:531 is a genuine 2-hop sweep (build.cuh header), which only the
+  // EXACT kernels compute; the batched builder would link ef_construction instead of m neighbours per node
+  if (mode == HNSW_BUILD_EXACT || ef_construction < m) {
     if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)rest * (m_max_0 + 8) * 2 + 4096))) return rc;
     rc = add_exact(first + start, rest, want_touched);
     if (!rc) node_count += rest;

@@ -64,6 +64,42 @@ def test_exact_build_equals_oracle_graph(name, n):
     assert st["inserts"] == n - 1 and st["reprunes"] > 0
 
 
+@pytest.mark.parametrize("dim,m,efc,n,dataset", [
+    (128, 16, 8, 2500, "lowrank"),     # staged kernels (insert_exact2_kernel)
+    (32, 12, 5, 2000, "uniform"),      # staged, 32-d rows
+    (20, 6, 3, 1200, "uniform"),       # scalar metric (insert_exact_kernel, the kernel the generic dims share)
+])
+def test_exact_build_with_ef_construction_below_m(dim, m, efc, n, dataset):
+    """ef_construction < m: w comes back full with fewer than m entries, so select_neighbors' candidate extension
+    (core.rs:698-721) is NOT redundant — nodes the search turned away only because w was full are linked until m are
+    selected.  Graph identical to the oracle's, single adds included; FAST requests run the exact builder here.
+    (Seeds are fixed to builds without a tie AT a selection cut: with ef_construction this small a 96-d uniform build
+    (seed 5) hits sim(291, 1182) == sim(291, 1002) exactly at rank 20/21 of a re-selection, where the reference leaves
+    the order to BinaryHeap internals — the parity definition excludes such ties)"""
+    import redis_hnsw_b200 as r
+
+    x, q = (data.lowrank(n + 40, dim, r=16, seed=5, n_queries=200) if dataset == "lowrank"
+            else data.uniform(n + 40, dim, seed=5, n_queries=200))
+    levels = data.draw_levels(n + 40, m, seed=6)
+    orc = oracle.Oracle(dim, m, efc)
+    orc.add_batch(x[:n], levels[:n])
+    go = orc.export_graph()
+    deg = np.diff(go["row_offs"])
+    assert deg.max() > efc, "the case must exercise the extension (a node with more than ef_construction links)"
+    for mode in (r.BUILD_EXACT, r.BUILD_FAST):
+        dev = r.DeviceIndex(dim, m, efc)
+        dev.add_batch(x[:n], levels[:n], mode=mode)
+        _assert_same_graph(dev.export_graph(), go)
+    longest = 0
+    for i in range(n, n + 40):          # NODE.ADD one at a time on the last index
+        assert dev.add(x[i], int(levels[i])) == orc.add(x[i], int(levels[i]))
+        assert sorted(dev.touched()) == sorted(orc.touched())
+        longest = max(longest, len(orc.node_neighbors(i, 0)))
+    assert longest > efc                # a fresh node linked more neighbours than w held: the extension was exercised
+    _assert_same_graph(dev.export_graph(), orc.export_graph())
+    assert_search_parity(dev, orc, q, 10, 32)
+
+
 def test_exact_build_in_pieces_and_single_adds_report_touched_nodes():
     """add_batch in several calls, then NODE.ADD one at a time: same graph, and the touched set equals what the
     reference reports through update_fn (core.rs:522,535-537,570-572,580-584)."""
