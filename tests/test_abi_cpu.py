@@ -119,3 +119,23 @@ def test_header_is_plain_c99(tmp_path):
     assert rc in ("0", "5")            # 5 = HNSW_ERR_CUDA on a machine without a device: loud failure, no fallback
     if rc == "5":
         assert "CUDA" in rest or "device" in rest
+
+
+def test_bench_stdout_carries_only_the_json_line(tmp_path):
+    """bench.py's contract is ONE JSON line on stdout; libraries that print banners on fd 1 (NCCL's version line at
+    N > 1) must not end up next to it: after claim_stdout() fd 1 points at stderr and emit() writes to the real stdout."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "bench.claim_stdout()\n"
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n')\n"      # what a C library does
+            "print('a python print')\n"
+            "bench.emit({'metric': 'x', 'value': 1})\n" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "x", "value": 1}
+    assert "NCCL version" in out.stderr and "a python print" in out.stderr
