@@ -139,3 +139,34 @@ def test_bench_stdout_carries_only_the_json_line(tmp_path):
     lines = out.stdout.splitlines()
     assert len(lines) == 1 and json.loads(lines[0]) == {"metric": "x", "value": 1}
     assert "NCCL version" in out.stderr and "a python print" in out.stderr
+
+
+def test_null_handle_and_bad_arguments_fail_cleanly(built):
+    """"The library never aborts" (include/hnsw_b200.h): every entry point taking an index answers HNSW_ERR_INVALID for a
+    NULL handle, create() rejects bad parameters before touching a device, and hnsw_last_error() carries the text."""
+    from redis_hnsw_b200 import _lib
+
+    L = _lib.lib()
+    null = C.c_void_p(0)
+    for name, (res, args) in _lib.SYMBOLS.items():
+        if not args or args[0] is not _lib._vp or name == "hnsw_index_destroy":
+            continue
+        call_args = [null]
+        for a in args[1:]:
+            if a in (C.c_uint32, C.c_uint64, C.c_int, C.c_int32, C.c_int64):
+                call_args.append(a(1))
+            elif a is C.c_char_p:
+                call_args.append(b"row_copy")
+            else:
+                call_args.append(None)      # NULL pointer
+        assert getattr(L, name)(*call_args) == _lib.ERR_INVALID, name
+        assert b"null index handle" in L.hnsw_last_error(), name
+    L.hnsw_index_destroy(null)              # a no-op, like free(NULL)
+    out = C.c_void_p(0)
+    for dim, m, efc in ((0, 16, 200), (128, 0, 200), (128, 16, 0), (128, 16, 513)):
+        assert L.hnsw_index_create(dim, m, efc, -1, C.byref(out)) == _lib.ERR_INVALID
+        assert not out.value
+    assert L.hnsw_index_create(128, 16, 200, -1, None) == _lib.ERR_INVALID
+    assert L.hnsw_l2_batch(None, None, 4, 32, None, -1) == _lib.ERR_INVALID
+    assert L.hnsw_l2_batch(None, None, 0, 32, None, -1) == _lib.HNSW_OK       # nothing to do
+    assert L.hnsw_version().startswith(b"hnsw_b200")
