@@ -52,6 +52,15 @@ def test_sharded_search_gloo_world2(tmp_path, nq):
     assert r0[1] == 0 and r0[2] == r1[1] and r1[2] == nq   # contiguous, complete, disjoint slices
 
 
+def test_sharded_search_gloo_world3_with_an_empty_rank(tmp_path):
+    """Fewer queries than ranks: a rank with an empty slice still takes part in the gather."""
+    port = _free_port()
+    mp.spawn(_worker, args=(3, port, 2, str(tmp_path)), nprocs=3, join=True)
+    res = [np.load(tmp_path / ("r%d.npy" % r)) for r in range(3)]
+    assert all(r[0] == 1 for r in res)
+    assert [int(r[2] - r[1]) for r in res] == [1, 1, 0]
+
+
 def test_query_slice_partitions():
     from redis_hnsw_b200 import sharding
 
