@@ -7,7 +7,10 @@
 // Parity pinning: the reference is Rust and cannot be compiled in this environment (no rustc/cargo),
 // so this restatement is pinned against the reference's own known-answer tests
 // (src/hnsw/metrics_tests.rs:4-33 and src/hnsw/core_tests.rs:7-81, see tests/test_oracle_kat.py) and
-// reviewed line by line against the cited reference lines below.
+// reviewed line by line against the cited reference lines below.  Second pin: tests/pyref_hnsw.py is an independent
+// pure-Python transliteration of core.rs (with Rust's BinaryHeap sift rules); tests/test_pyref_cross_check.py requires
+// both restatements to agree on graphs (list order included), update_fn sets, deletes and search results, on
+// continuous data and on grid data where almost every comparison is a tie.
 //
 // What is restated (reference file:line):
 //   metrics.rs:14-23   euclidean()        -> orc_euclidean  (AVX2 path iff dim % 32 == 0, else scalar)
