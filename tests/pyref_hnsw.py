@@ -95,6 +95,51 @@ def sim_func_euc(a, b):
     return F32(-acc)
 
 
+# ---------------------------------------------------------------- metrics.rs:25-77 (the AVX2 + FMA path; dim % 32 == 0)
+def _round_f32(fr):
+    """Correctly rounded (nearest, ties to even) f32 of an exact rational; normal range only."""
+    from fractions import Fraction
+
+    if fr == 0:
+        return F32(0.0)
+    neg = fr < 0
+    fr = -fr if neg else fr
+    e = fr.numerator.bit_length() - fr.denominator.bit_length()
+    if Fraction(2) ** e > fr:
+        e -= 1
+    assert Fraction(2) ** e <= fr < Fraction(2) ** (e + 1) and -126 <= e <= 127
+    scaled = fr / Fraction(2) ** (e - 23)          # in [2^23, 2^24)
+    n = scaled.numerator // scaled.denominator
+    rem = scaled - n
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (n & 1)):
+        n += 1
+    v = float(n) * 2.0 ** (e - 23)                 # exact in f64
+    return F32(-v if neg else v)
+
+
+def _fma_f32(a, b, c):
+    """_mm256_fmadd_ps lane: a * b + c with ONE rounding (exact rational arithmetic, then round to f32)."""
+    from fractions import Fraction
+
+    return _round_f32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def sim_func_avx_euc(a, b):
+    """metrics.rs:48-77: four 8-lane accumulators fed by fused multiply-adds over blocks of 32 floats, then
+    (euc1 + euc2) + (euc3 + euc4) (:71-74), low 128 + high 128 (:37-39), and hsum_ps_sse3 (:25-32): (v0 + v1) + (v2 + v3)."""
+    n = len(a)
+    assert n % 32 == 0
+    euc = [[F32(0.0)] * 8 for _ in range(4)]
+    for i in range(0, n, 32):
+        for k in range(4):
+            for j in range(8):
+                d = F32(F32(a[i + 8 * k + j]) - F32(b[i + 8 * k + j]))
+                euc[k][j] = _fma_f32(d, d, euc[k][j])
+    v = [F32(F32(euc[0][j] + euc[1][j]) + F32(euc[2][j] + euc[3][j])) for j in range(8)]
+    lo = [F32(v[j] + v[j + 4]) for j in range(4)]
+    return F32(-F32(F32(lo[0] + lo[1]) + F32(lo[2] + lo[3])))
+
+
 class _Node:
     def __init__(self, data):
         self.data = np.asarray(data, dtype=F32)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from pyref_hnsw import PyRefIndex, RustHeap
+from pyref_hnsw import PyRefIndex, RustHeap, sim_func_avx_euc, sim_func_euc
 from redis_hnsw_b200 import data
 
 
@@ -107,3 +107,20 @@ def test_rust_binary_heap_model_against_known_traces():
         r.push(item)
     assert r.peek() == (1.0, 2)
     assert r.pop() == (1.0, 2) and r.pop() == (1.0, 4) and r.pop() == (2.0, 3)
+
+
+@pytest.mark.parametrize("dim,rows", [(32, 60), (128, 40), (768, 8)])
+def test_avx_fma_metric_order_against_exact_rational_emulation(dim, rows):
+    """metrics.rs:48-77 restated with exact rational arithmetic (every FMA rounded once, adds in the reference's tree)
+    must give the oracle's bits — the same bits the CUDA kernels are tested against (tests/test_gpu_metric.py)."""
+    rng = np.random.default_rng(dim)
+    a = (rng.standard_normal((rows, dim)) * 3).astype(np.float32)
+    b = (rng.standard_normal((rows, dim)) * 3).astype(np.float32)
+    got = oracle.euclidean_batch(a, b)
+    want = np.array([sim_func_avx_euc(a[i], b[i]) for i in range(rows)], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # and the scalar path on a non-x32 dimension (metrics.rs:79-84)
+    a2, b2 = a[:, :dim - 1], b[:, :dim - 1]
+    got2 = oracle.euclidean_batch(np.ascontiguousarray(a2), np.ascontiguousarray(b2))
+    want2 = np.array([sim_func_euc(a2[i], b2[i]) for i in range(rows)], dtype=np.float32)
+    assert np.array_equal(got2.view(np.uint32), want2.view(np.uint32))
