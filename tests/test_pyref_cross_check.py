@@ -124,3 +124,32 @@ def test_avx_fma_metric_order_against_exact_rational_emulation(dim, rows):
     got2 = oracle.euclidean_batch(np.ascontiguousarray(a2), np.ascontiguousarray(b2))
     want2 = np.array([sim_func_euc(a2[i], b2[i]) for i in range(rows)], dtype=np.float32)
     assert np.array_equal(got2.view(np.uint32), want2.view(np.uint32))
+
+
+@pytest.mark.parametrize("level_seed", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_python_transliteration_passes_the_reference_kat(level_seed):
+    """The reference's own test (core_tests.rs:7-81) replayed on the transliteration, for several level draws (the
+    reference seeds its RNG from entropy, so the KAT must hold for any): 100 nodes [i; 4], m = 5, efCon = 16; query
+    [10; 4], k = 5 -> sims 0, -4, -4, -16, -16 with node10 first; then every node is deleted in insertion order and no
+    layer set or adjacency list may still mention it."""
+    n, dim = 100, 4
+    ref = PyRefIndex(dim, 5, 16)
+    orc = oracle.Oracle(dim, 5, 16)
+    levels = data.draw_levels(n, 5, seed=level_seed)
+    for i in range(n):
+        v = np.full(dim, float(i), np.float32)
+        assert ref.add_node(v, int(levels[i])) == orc.add(v, int(levels[i])) == i
+    assert ref.node_count == n and ref.enterpoint is not None
+    ids, sims = ref.search_knn(np.full(dim, 10.0, np.float32), 5)
+    assert len(ids) == 5 and ids[0] == 10
+    assert [float(s) for s in sims] == [0.0, -4.0, -4.0, -16.0, -16.0]
+    oi, osim = orc.search(np.full(dim, 10.0, np.float32), 5)
+    assert oi.tolist() == ids and [float(s) for s in osim] == [float(s) for s in sims]
+    for i in range(n):
+        ref.delete_node(i)
+        orc.delete(i)
+        assert ref.node_count == n - i - 1 and i not in ref.nodes
+        assert all(i not in layer for layer in ref.layers)
+        assert all(i not in lst for node in ref.nodes.values() for lst in node.neighbors)
+        assert orc.params()["node_count"] == ref.node_count
+    assert ref.enterpoint is None
