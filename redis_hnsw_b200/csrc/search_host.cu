@@ -154,6 +154,27 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   while ((1u << slot_bits) < slots) ++slot_bits;
   // 16-bit tags identify an id exactly only below 2^(log2(slots) + 15)
   const bool tag16 = opt_recent_tag != 32 && slot_bits + 15 < 32 && n_ids <= (1ull << (slot_bits + 15));
+  if (opt_search_cta && nq <= 4ull * (uint64_t)num_sms) {  // DRAFT: one query per CTA of 4 warps (search2.cuh, COPY == 2)
+    const size_t smem_cta = warp2_smem_bytes(dim, 32, slots, tag16 ? 2 : 4) + 256;
+    if (smem_cta <= max_smem) {
+      int rc0 = ensure_scratch(s_ctl, std::max<size_t>(64 + (size_t)nq * 4, 64 * kCtlSlots));
+      if (rc0) return rc0;
+      SearchArgs ac{};
+      ac.queries = d_q;
+      ac.nq = (uint32_t)nq;
+      ac.k = k;
+      ac.ef = ef;
+      ac.ids = d_ids;
+      ac.sims = d_sims;
+      ac.counts = d_counts;
+      ac.stats = d_stats;
+      ac.vis_slots = slots;
+      LaunchCfg cc{(int)nq, 128, smem_cta, s};
+      cudaError_t ec = run(kind, kKernSearch2Cta + (tag16 ? 1 : 0), efr, cc, g, &ac);
+      if (ec != cudaSuccess) return cuda_fail(ec, "search_knn2_cta launch");
+      return HNSW_OK;
+    }
+  }
   const size_t per_warp = warp2_smem_bytes(dim, S, slots, tag16 ? 2 : 4);
   int block = opt_block ? std::min(opt_block, 128) : 64;  // search_knn2_kernel is bounded at 128 threads per CTA
   while (block > 32 && (size_t)(block / 32) * per_warp > max_smem) block /= 2;

@@ -77,6 +77,26 @@ def test_latency_mode_parity(name, efs):
     dev.set_option("row_copy", 0)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,efs", [("cfg1_10k_d32_m5", (1, 16, 100)), ("d128_m16", (8, 64, 200, 512)), ("d768_m32", (16, 128))])
+def test_cta_latency_kernel_parity(name, efs):
+    """DRAFT (branch r2-cta-draft): option search_cta = 1 runs one query per CTA of 4 warps for small calls
+    (search_knn2_cta_kernel).  First thing to run on hardware next round — under a timeout: two named barriers per round."""
+    c = case(name)
+    dev = device_index(name)
+    dev.set_option("search_cta", 1)
+    for ef in efs:
+        for lo, n in ((0, 1), (1, 7), (8, 100)):
+            q = c["q"][lo:lo + n]
+            oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=ef)
+            ok = ost[:, 3] == 0
+            ids, sims, counts = dev.search_batch(q, 10, ef=ef)
+            assert np.array_equal(counts, ocounts)
+            assert np.array_equal(ids[ok], oids[ok])
+            assert np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
+    dev.set_option("search_cta", 0)
+
+
 def test_default_ef_is_ef_construction():
     """core.rs:485: search_knn always searches with ef = ef_construction."""
     c = case("cfg1_10k_d32_m5")
