@@ -644,6 +644,9 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
   } else if (n == "row_copy") {
     if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "row_copy must be 0 (bulk-async copies everywhere) or 1 (cp.async for 32-d / 128-d rows)");
     ix.opt_row_copy = (int)value;
+  } else if (n == "recent_ways") {
+    if (value != 1 && value != 2) return fail(HNSW_ERR_INVALID, "recent_ways must be 1 or 2");
+    ix.opt_recent_ways = (int)value;
   } else if (n == "search_cta") {
     if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "search_cta must be 0 or 1");
     ix.opt_search_cta = (int)value;

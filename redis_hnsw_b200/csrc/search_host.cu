@@ -183,7 +183,13 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   if (smem > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the staged search kernel");
   // rows of up to two cp.async instructions (32-d, 128-d) are copied with cp.async, longer ones with bulk-async copies
   const bool cp = opt_row_copy == 1 && (kind == kKindR4 || kind == kKindR1);
-  const int id = search2_id(S, tag16) + (cp ? kKernSearch2Cp - kKernSearch2 : 0);
+  int id = search2_id(S, tag16) + (cp ? kKernSearch2Cp - kKernSearch2 : 0);
+  uint32_t table_slots = slots;
+  if (opt_recent_ways == 2 && cp && tag16 && slots >= 128 && n_ids <= (1ull << (slot_bits - 1 + 15))) {
+    // DRAFT: the same bytes as `slots` 16-bit tags, organised as slots / 2 two-way sets (one 32-bit word per set)
+    table_slots = slots / 2;
+    id = kKernSearch2W2 + (S == 4 ? 0 : S == 8 ? 1 : S == 16 ? 2 : 3);
+  }
   int occ = occupancy(kind, id, efr, block, smem);
   if (occ < 1) return fail(HNSW_ERR_CUDA, "staged search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
@@ -205,7 +211,7 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   a.stats = d_stats;
   a.work_counter = ctl + 0;
   a.retry_count = ctl + 2;
-  a.vis_slots = slots;
+  a.vis_slots = table_slots;
   LaunchCfg c{grid, block, smem, s};
   e = run(kind, id, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "search_knn2 launch");

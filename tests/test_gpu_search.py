@@ -97,6 +97,28 @@ def test_cta_latency_kernel_parity(name, efs):
     dev.set_option("search_cta", 0)
 
 
+@pytest.mark.parametrize("name", ["cfg1_10k_d32_m5", "d128_m16"])
+def test_two_way_visited_sets_parity(name):
+    """DRAFT (branch r2-cta-draft): option recent_ways = 2 (Recent<Way2>): same results, fewer or equal re-evaluations."""
+    c = case(name)
+    dev = device_index(name)
+    q = c["q"][:300]
+    oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=64)
+    ok = ost[:, 3] == 0
+    evals = {}
+    for ways in (1, 2):
+        dev.set_option("search_impl", 2)
+        dev.set_option("recent_ways", ways)
+        ids, sims, counts, st = dev.search_batch(q, 10, ef=64, stats=True)
+        assert np.array_equal(ids[ok], oids[ok]) and np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
+        assert np.array_equal(counts, ocounts)
+        assert np.array_equal(st[ok, 1:3].astype(np.uint64), ost[ok, 1:3]) and np.all(st[ok, 0] >= ost[ok, 0])
+        evals[ways] = int(st[ok, 0].sum())
+    dev.set_option("search_impl", 0)
+    dev.set_option("recent_ways", 1)
+    assert evals[2] <= evals[1] * 1.01
+
+
 def test_default_ef_is_ef_construction():
     """core.rs:485: search_knn always searches with ef = ef_construction."""
     c = case("cfg1_10k_d32_m5")
