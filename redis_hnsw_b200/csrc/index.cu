@@ -403,7 +403,7 @@ int hnsw_index_create(uint32_t data_dim, uint32_t m, uint32_t ef_construction, i
   if (!out) return fail(HNSW_ERR_INVALID, "null out pointer");
   *out = nullptr;
   if (data_dim == 0 || m == 0 || ef_construction == 0) return fail(HNSW_ERR_INVALID, "dim, m and ef_construction must be > 0");
-  if (efr_for(ef_construction) == 0) return fail(HNSW_ERR_INVALID, "ef_construction > 512 is not supported");
+  if (efr_for(ef_construction) == 0) return fail(HNSW_ERR_INVALID, "ef_construction > 1024 is not supported");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(HNSW_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));

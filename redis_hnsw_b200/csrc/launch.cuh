@@ -23,6 +23,7 @@ inline int efr_for(uint32_t ef) {
   if (ef <= 128) return 4;
   if (ef <= 256) return 8;
   if (ef <= 512) return 16;
+  if (ef <= 1024) return 32;  // DRAFT (branch): 64 list registers per lane
   return 0;
 }
 
@@ -146,6 +147,7 @@ cudaError_t run_kind(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, 
     case 4: return run_kernel<4, Dist>(id, c, ka, occupancy_only, occ);
     case 8: return run_kernel<8, Dist>(id, c, ka, occupancy_only, occ);
     case 16: return run_kernel<16, Dist>(id, c, ka, occupancy_only, occ);
+    case 32: return run_kernel<32, Dist>(id, c, ka, occupancy_only, occ);
   }
   return cudaErrorInvalidValue;
 }

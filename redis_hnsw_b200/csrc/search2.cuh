@@ -458,7 +458,7 @@ __device__ __forceinline__ unsigned char* warp2_setup(Warp2<C, S, T>& w, unsigne
 // there only adds spills (measured: 256 k -> 232 k QPS at 1M x 768, ef = 200), so large C keeps 128 registers.
 template <int EFR, int C = 4>
 struct Search2Bounds {
-  static constexpr int kMinBlocks = C > 8 ? 4 : (EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6));
+  static constexpr int kMinBlocks = EFR >= 32 ? 3 : (C > 8 ? 4 : (EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6)));
 };
 
 template <int EFR, int C, int S, class T, int COPY = 0>

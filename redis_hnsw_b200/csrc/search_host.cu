@@ -65,7 +65,7 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   if (k == 0) return fail(HNSW_ERR_INVALID, "k must be > 0");
   if (ef == 0) ef = ef_construction;  // core.rs:485
   const int efr = efr_for(ef);
-  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..1024)", ef);
   const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
   last_search_staged = staged_kind && opt_search_impl != 1 && (opt_search_impl == 2 || !d_stats);
   if (last_search_staged) return search_device2(nq, d_q, k, ef, efr, d_ids, d_sims, d_counts, d_stats, s);
@@ -326,7 +326,7 @@ int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uin
 int Index::search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
                              uint32_t* n_out) {
   const int efr = efr_for(ef);
-  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..1024)", ef);
   if (ep >= n_ids || h_level[ep] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", ep);
   const uint32_t slots = next_pow2(std::max<uint64_t>(65536, (uint64_t)ef * 512));
   int rc = ensure_scratch(s_vis, (size_t)slots * 4);

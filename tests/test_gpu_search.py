@@ -119,6 +119,25 @@ def test_two_way_visited_sets_parity(name):
     assert evals[2] <= evals[1] * 1.01
 
 
+def test_ef_up_to_1024():
+    """DRAFT (branch r2-cta-draft): a sixth list class (32 registers per lane x 2) lifts the ef / ef_construction limit
+    from 512 to 1024 — search parity at ef 600 / 1024 and an exact build with ef_construction = 700."""
+    import oracle
+    import redis_hnsw_b200 as r
+
+    c = case("d128_m16")
+    dev = device_index("d128_m16")
+    for ef in (600, 1024):
+        assert_search_parity(dev, c["oracle"], c["q"][:200], 10, ef)
+    n = 1500
+    orc = oracle.Oracle(c["dim"], c["m"], 700)
+    orc.add_batch(c["x"][:n], c["levels"][:n])
+    d2 = r.DeviceIndex(c["dim"], c["m"], 700)
+    d2.add_batch(c["x"][:n], c["levels"][:n], mode=r.BUILD_EXACT)
+    go, gd = orc.export_graph(), d2.export_graph()
+    assert np.array_equal(go["row_offs"], gd["row_offs"]) and np.array_equal(go["nbrs"], gd["nbrs"])
+
+
 def test_default_ef_is_ef_construction():
     """core.rs:485: search_knn always searches with ef = ef_construction."""
     c = case("cfg1_10k_d32_m5")
