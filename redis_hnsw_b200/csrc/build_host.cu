@@ -74,7 +74,7 @@ bool Index::exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) c
 int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
   if (count == 0) return HNSW_OK;
   const int efr = build_efr(*this);
-  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
   if (!exact_vis_slots) exact_vis_slots = next_pow2(std::max<uint64_t>(1u << 16, (uint64_t)ef_construction * 256));
   const uint32_t lcap = list_capacity(g.W);
   const uint32_t touched_cap = want_touched ? 1u << 16 : 0;
@@ -419,7 +419,7 @@ int Index::add_fast(uint32_t first, uint32_t count) {
 int Index::delete_node(uint32_t id) {
   if (id >= n_ids || h_level[id] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", id);  // core.rs:421
   const int efr = efr_for(m_max_0);  // delete only re-selects lists of at most m_max_0 entries
-  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
   int rc = pull_meta();  // the device owns pool_used
   if (rc) return rc;
   const uint32_t lcap = list_capacity(g.W);
@@ -508,7 +508,7 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
   if (!data) return fail(HNSW_ERR_INVALID, "null data");
   if (mode != HNSW_BUILD_EXACT && mode != HNSW_BUILD_FAST) return fail(HNSW_ERR_INVALID, "unknown build mode %d", mode);
   if (n_ids + count >= 0x7FFFFFFFull) return fail(HNSW_ERR_INVALID, "too many nodes");
-  if (!build_efr(*this)) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 512)");
+  if (!build_efr(*this)) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
   int rc = pull_meta();  // the device owns pool_used
   if (rc) return rc;
   const uint32_t first = (uint32_t)n_ids;

@@ -403,7 +403,7 @@ int hnsw_index_create(uint32_t data_dim, uint32_t m, uint32_t ef_construction, i
   if (!out) return fail(HNSW_ERR_INVALID, "null out pointer");
   *out = nullptr;
   if (data_dim == 0 || m == 0 || ef_construction == 0) return fail(HNSW_ERR_INVALID, "dim, m and ef_construction must be > 0");
-  if (efr_for(ef_construction) == 0) return fail(HNSW_ERR_INVALID, "ef_construction > 512 is not supported");
+  if (efr_for(ef_construction) == 0) return fail(HNSW_ERR_INVALID, "ef_construction > 1024 is not supported");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(HNSW_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
@@ -644,6 +644,12 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
   } else if (n == "row_copy") {
     if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "row_copy must be 0 (bulk-async copies everywhere) or 1 (cp.async for 32-d / 128-d rows)");
     ix.opt_row_copy = (int)value;
+  } else if (n == "recent_ways") {
+    if (value != 1 && value != 2) return fail(HNSW_ERR_INVALID, "recent_ways must be 1 or 2");
+    ix.opt_recent_ways = (int)value;
+  } else if (n == "search_cta") {
+    if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "search_cta must be 0 or 1");
+    ix.opt_search_cta = (int)value;
   } else if (n == "build_batch") {
     if (value < 1) return fail(HNSW_ERR_INVALID, "build_batch must be >= 1");
     ix.opt_build_batch = (uint32_t)value;

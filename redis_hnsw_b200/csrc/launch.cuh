@@ -23,6 +23,7 @@ inline int efr_for(uint32_t ef) {
   if (ef <= 128) return 4;
   if (ef <= 256) return 8;
   if (ef <= 512) return 16;
+  if (ef <= 1024) return 32;  // DRAFT (branch): 64 list registers per lane
   return 0;
 }
 
@@ -42,6 +43,8 @@ enum KernelId : int {
 // build_search2_kernel (TMA-staged K1 of the batched builder): id = kKernBuildSearch2 + (16-bit visited tags ? 1 : 0)
 constexpr int kKernSearch2Cp = 24;  // search_knn2_kernel with cp.async row copies (RowCopy<C>::kOk): + 2 * log2(S / 4) + (16-bit tags ? 1 : 0)
 constexpr int kKernBuildSearch2 = 32;
+constexpr int kKernSearch2W2 = 52;   // DRAFT search_knn2_kernel, cp.async rows, 2-way visited sets: + log2(S / 4)
+constexpr int kKernSearch2Cta = 48;  // DRAFT search_knn2_cta_kernel (one query per CTA of 4 warps): + (16-bit tags ? 1 : 0)
 constexpr int kKernExact2 = 40;   // insert_exact2_kernel / delete_exact2_kernel (TMA-staged, build2.cuh)
 constexpr int kKernDelete2 = 41;
 constexpr int kKernExact2Small = 42;
@@ -117,6 +120,12 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
       case kKernSearch2Cp + 5: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, uint16_t, 1>), SearchArgs) break;
       case kKernSearch2Cp + 6: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint32_t, 1>), SearchArgs) break;
       case kKernSearch2Cp + 7: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, uint16_t, 1>), SearchArgs) break;
+      case kKernSearch2W2 + 0: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, Way2, 1>), SearchArgs) break;
+      case kKernSearch2W2 + 1: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, Way2, 1>), SearchArgs) break;
+      case kKernSearch2W2 + 2: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, Way2, 1>), SearchArgs) break;
+      case kKernSearch2W2 + 3: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, Way2, 1>), SearchArgs) break;
+      case kKernSearch2Cta + 0: HNSW_RUN((search_knn2_cta_kernel<EFR, Dist::C, uint32_t>), SearchArgs)
+      case kKernSearch2Cta + 1: HNSW_RUN((search_knn2_cta_kernel<EFR, Dist::C, uint16_t>), SearchArgs)
       case kKernBuildSearch2 + 0: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
       case kKernBuildSearch2 + 1: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint16_t>), FastArgs)
       case kKernBuildReprune2 + 0: HNSW_RUN((build_reprune2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
@@ -138,6 +147,7 @@ cudaError_t run_kind(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, 
     case 4: return run_kernel<4, Dist>(id, c, ka, occupancy_only, occ);
     case 8: return run_kernel<8, Dist>(id, c, ka, occupancy_only, occ);
     case 16: return run_kernel<16, Dist>(id, c, ka, occupancy_only, occ);
+    case 32: return run_kernel<32, Dist>(id, c, ka, occupancy_only, occ);
   }
   return cudaErrorInvalidValue;
 }

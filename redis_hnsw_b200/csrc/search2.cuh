@@ -155,6 +155,37 @@ struct Recent {
   }
 };
 
+// DRAFT (not run on hardware): two-way set-associative flavour in the same shared memory.  A set is one 32-bit word
+// holding two 16-bit exact tags, most recent in the low half; a miss moves the newcomer to the front and drops the older
+// of the two (a 2-entry LRU).  Same exactness argument as the 16-bit direct-mapped table: (set, tag) determines the id for
+// ids < 2^(log2(sets) + 15).  Aim: fewer forgotten ids -> fewer of the 6 % re-evaluations.
+struct Way2 {
+  uint32_t w;
+};
+template <>
+struct Recent<Way2> {
+  Way2* tab;
+  uint32_t n16;   // table bytes / 16
+  int bits;       // log2(sets)
+  __device__ __forceinline__ void clear(int lane) {
+    __syncwarp();
+    uint4 e = make_uint4(0u, 0u, 0u, 0u);
+    uint4* t = reinterpret_cast<uint4*>(tab);
+    for (uint32_t i = lane; i < n16; i += 32) t[i] = e;
+    __syncwarp();
+  }
+  __device__ __forceinline__ bool test_and_set(uint32_t nid) {
+    const uint32_t f = (nid * 2654435761u) & ((1u << (bits + 15)) - 1u);
+    const uint32_t set = f >> 15;
+    const uint32_t tag = 0x8000u | (f & 0x7FFFu);
+    const uint32_t cur = tab[set].w;
+    const uint32_t t0 = cur & 0xFFFFu, t1 = cur >> 16;
+    if (t0 == tag) return false;
+    tab[set].w = (t0 << 16) | tag;  // newcomer (or the hit in way 1) moves to the front
+    return t1 != tag;
+  }
+};
+
 template <int EFR>
 __device__ __forceinline__ bool list_has(const CandList<EFR>& L, uint32_t x) {
   bool hit = false;
@@ -175,6 +206,8 @@ struct Warp2 {
   uint32_t bar;        // shared-space address of the mbarrier
   uint32_t parity;
   Recent<T> seen;
+  float* sims;         // COPY == 2 (CTA-cooperative rounds): [32] sims of the round's rows
+  uint32_t* ctl;       // COPY == 2: ctl[0] = rows of the round (kEmpty = the query is finished)
 };
 
 // per-lane partial of one staged row (lane-permuted layout: group g of V chunks at float-V index g*32 + lane)
@@ -206,6 +239,40 @@ __device__ __forceinline__ float staged_partial(const float (&q)[C], const float
 
 // Evaluate the ids flagged new (lane j holds nb) and apply them to the list in lane order (= adjacency-list order,
 // core.rs:646-667).  `adj_prefetch` = base of the level-0 adjacency rows (or null) for the L2 prefetch of admitted ids.
+// ---------------------------------------------------------------- CTA-cooperative rounds (COPY == 2)  -- DRAFT
+// One query per CTA of 4 warps.  Warp 0 owns the search (list, visited table, adjacency walk); for every round it
+// publishes the compacted ids, and all four warps copy, multiply and reduce 8 rows each, so the ~450 dependent
+// instructions a 32-row round costs one warp (copies 147, partials 200, reduction 96; profiles/r1e_search.md) shrink
+// to ~120 on the critical path.  Two named barriers per round.  NOT YET RUN ON HARDWARE.
+__device__ __forceinline__ void cta_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+template <int C, int S, class T>
+__device__ __forceinline__ void cta_round(const Graph& g, Warp2<C, S, T>& w, int nr, int wi, int lane) {
+  static_assert(S == 32, "4 warps x 8 rows");
+  constexpr int RPW = 8;
+  constexpr int V = RowRegs<C>::V;
+  constexpr uint32_t RB = Warp2<C, S, T>::kRowBytes;
+  const int r0 = wi * RPW;
+  if (r0 >= nr) return;
+#pragma unroll
+  for (int j = 0; j < RPW; ++j) {
+    const int r = r0 + j;
+    const uint32_t rid = w.ids[r];                         // stale beyond nr (copy predicated off)
+    const float* src = g.vecs + (size_t)rid * (32 * C) + lane * V;
+#pragma unroll
+    for (int q = 0; q < C / V; ++q)
+      cp_async_if<4 * V>(w.stage_s + (uint32_t)r * RB + (uint32_t)(q * 128 * V) + (uint32_t)(lane * 4 * V), src + q * 32 * V, r < nr);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  float acc[RPW];
+  const float* st = reinterpret_cast<const float*>(w.stage);
+#pragma unroll
+  for (int j = 0; j < RPW; ++j) acc[j] = staged_partial<C>(w.q, st + (size_t)(r0 + j) * (32 * C), lane);
+  const float s = reduce_rows<RPW>(acc, lane);            // lane j < 8 holds row r0 + j
+  if (lane < RPW) w.sims[r0 + lane] = s;
+}
+
 // rows per unconditional group of eval_and_admit: about 32 floats of row data per lane, a power of two, 1 <= G <= min(S, 8)
 __host__ __device__ constexpr int partial_group(int C, int S) {
   int g = 1;
@@ -237,6 +304,15 @@ __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w
   for (int base = 0; base < n_new; base += S) {
     const int nr = min(S, n_new - base);
     __syncwarp();  // the previous round's reads of the stage and of ids[] are complete
+    float s;
+    if constexpr (COPY == 2) {
+      if (mine_new && rank >= base && rank < base + nr) w.ids[rank - base] = nb;
+      if (lane == 0) w.ctl[0] = (uint32_t)nr;
+      cta_bar(1);                                          // ids and nr are published: the other warps start
+      cta_round<C, S, T>(g, w, nr, 0, lane);
+      cta_bar(2);                                          // every warp has written its sims
+      s = lane < nr ? w.sims[lane] : 0.0f;
+    } else {
     if constexpr (COPY == 0) {
       if (lane == 0) mbar_expect_tx(w.bar, (uint32_t)nr * RB);
       __syncwarp();
@@ -278,7 +354,8 @@ __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w
         for (int r = g0; r < g0 + G; ++r) acc[r] = 0.0f;
       }
     }
-    const float s = reduce_rows<S>(acc, lane);
+    s = reduce_rows<S>(acc, lane);
+    }
     const uint32_t id = (lane < nr) ? w.ids[lane] : kEmpty;
     uint32_t cand = __ballot_sync(kFull, lane < nr && L.admits(s, ef));
     while (cand) {
@@ -381,7 +458,7 @@ __device__ __forceinline__ unsigned char* warp2_setup(Warp2<C, S, T>& w, unsigne
 // there only adds spills (measured: 256 k -> 232 k QPS at 1M x 768, ef = 200), so large C keeps 128 registers.
 template <int EFR, int C = 4>
 struct Search2Bounds {
-  static constexpr int kMinBlocks = C > 8 ? 4 : (EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6));
+  static constexpr int kMinBlocks = EFR >= 32 ? 3 : (C > 8 ? 4 : (EFR <= 4 ? 8 : (EFR == 8 ? 7 : 6)));
 };
 
 template <int EFR, int C, int S, class T, int COPY = 0>
@@ -440,6 +517,81 @@ __global__ void __launch_bounds__(128, Search2Bounds<EFR, C>::kMinBlocks) search
     evals += cnt.n_dist;
   }
   if (lane == 0 && a.retry_count) atomicAdd(a.retry_count + 1, evals);  // ctl[3]: evaluations of the launch (low 32 bits)
+}
+
+// ---------------------------------------------------------------- one query per CTA (COPY == 2)  -- DRAFT, see cta_round
+// grid = nq, block = 128.  Shared memory: one Warp2 region with a 32-row stage | sims[32] | ctl.
+template <int EFR, int C, class T>
+__global__ void __launch_bounds__(128, 1) search_knn2_cta_kernel(Graph g, SearchArgs a) {
+  constexpr int S = 32;
+  extern __shared__ __align__(128) unsigned char smem2[];
+  const int lane = lane_id();
+  const int wi = threadIdx.x >> 5;
+  Warp2<C, S, T> w;
+  unsigned char* extra;
+  if (wi == 0) {
+    extra = warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane);   // tags are cleared per search_layer2, stage zeroed here
+  } else {                                                        // same pointers, no initialisation
+    w.stage = reinterpret_cast<const float4*>(smem2);
+    w.stage_s = smem_u32(smem2);
+    const uint32_t tab_bytes = (a.vis_slots * (uint32_t)sizeof(T) + 127u) & ~127u;
+    w.ids = reinterpret_cast<uint32_t*>(smem2 + (size_t)S * C * 128 + tab_bytes);
+    extra = smem2 + warp2_smem_bytes(32 * C, S, a.vis_slots, sizeof(T));
+  }
+  w.sims = reinterpret_cast<float*>(extra);
+  w.ctl = reinterpret_cast<uint32_t*>(extra + 128);
+  __syncthreads();
+  const uint32_t qi = blockIdx.x;
+  if (qi >= a.nq) return;                                         // whole CTA
+  const float* qn = a.queries + (size_t)qi * (32 * C);
+#pragma unroll
+  for (int c = 0; c < C; ++c) w.q[c] = qn[32 * c + lane];
+  if (wi != 0) {                                                  // workers: serve rounds until the owner says stop
+    for (;;) {
+      cta_bar(1);
+      const uint32_t nr = w.ctl[0];
+      if (nr == kEmpty) return;
+      cta_round<C, S, T>(g, w, (int)nr, wi, lane);
+      cta_bar(2);
+    }
+  }
+  CandList<EFR> L;
+  Counters cnt = {0, 0, 0};
+  const int32_t entry = g.meta[kMetaEntry];
+  uint32_t n_out = 0;
+  if (entry >= 0) {                                               // core.rs:481-483
+    uint32_t ep = (uint32_t)entry;
+    for (int lc = g.meta[kMetaMaxLayer]; lc >= 0; --lc) {         // core.rs:869-876
+      search_layer2<EFR, C, S, T, 2>(g, w, ep, lc > 0 ? 1 : (int)a.ef, (uint32_t)lc, L, cnt, lane);
+      float s;
+      if (lc > 0) L.get(0, lane, false, ep, s);
+    }
+    n_out = min((uint32_t)L.len, a.k);                            // core.rs:879
+  }
+  if (lane == 0) w.ctl[0] = kEmpty;                               // release the workers
+  cta_bar(1);
+#pragma unroll
+  for (int r = 0; r < EFR; ++r) {                                 // core.rs:878-891 nearest-first
+    uint32_t e = r * 32 + lane;
+    if (e < a.k) {
+      bool have = e < n_out;
+      a.ids[(size_t)qi * a.k + e] = have ? (L.id[r] & ~kExpanded) : kEmpty;
+      a.sims[(size_t)qi * a.k + e] = have ? L.sim[r] : -CUDART_INF_F;
+    }
+  }
+  for (uint32_t e = EFR * 32 + lane; e < a.k; e += 32) {
+    a.ids[(size_t)qi * a.k + e] = kEmpty;
+    a.sims[(size_t)qi * a.k + e] = -CUDART_INF_F;
+  }
+  if (lane == 0) {
+    a.counts[qi] = n_out;
+    if (a.stats) {
+      a.stats[(size_t)qi * 4 + 0] = cnt.n_dist;
+      a.stats[(size_t)qi * 4 + 1] = cnt.n_adj;
+      a.stats[(size_t)qi * 4 + 2] = cnt.n_hops;
+      a.stats[(size_t)qi * 4 + 3] = 4u;
+    }
+  }
 }
 
 }  // namespace hnsw

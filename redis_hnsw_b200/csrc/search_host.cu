@@ -65,7 +65,7 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   if (k == 0) return fail(HNSW_ERR_INVALID, "k must be > 0");
   if (ef == 0) ef = ef_construction;  // core.rs:485
   const int efr = efr_for(ef);
-  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..1024)", ef);
   const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
   last_search_staged = staged_kind && opt_search_impl != 1 && (opt_search_impl == 2 || !d_stats);
   if (last_search_staged) return search_device2(nq, d_q, k, ef, efr, d_ids, d_sims, d_counts, d_stats, s);
@@ -154,6 +154,27 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   while ((1u << slot_bits) < slots) ++slot_bits;
   // 16-bit tags identify an id exactly only below 2^(log2(slots) + 15)
   const bool tag16 = opt_recent_tag != 32 && slot_bits + 15 < 32 && n_ids <= (1ull << (slot_bits + 15));
+  if (opt_search_cta && nq <= 4ull * (uint64_t)num_sms) {  // DRAFT: one query per CTA of 4 warps (search2.cuh, COPY == 2)
+    const size_t smem_cta = warp2_smem_bytes(dim, 32, slots, tag16 ? 2 : 4) + 256;
+    if (smem_cta <= max_smem) {
+      int rc0 = ensure_scratch(s_ctl, std::max<size_t>(64 + (size_t)nq * 4, 64 * kCtlSlots));
+      if (rc0) return rc0;
+      SearchArgs ac{};
+      ac.queries = d_q;
+      ac.nq = (uint32_t)nq;
+      ac.k = k;
+      ac.ef = ef;
+      ac.ids = d_ids;
+      ac.sims = d_sims;
+      ac.counts = d_counts;
+      ac.stats = d_stats;
+      ac.vis_slots = slots;
+      LaunchCfg cc{(int)nq, 128, smem_cta, s};
+      cudaError_t ec = run(kind, kKernSearch2Cta + (tag16 ? 1 : 0), efr, cc, g, &ac);
+      if (ec != cudaSuccess) return cuda_fail(ec, "search_knn2_cta launch");
+      return HNSW_OK;
+    }
+  }
   const size_t per_warp = warp2_smem_bytes(dim, S, slots, tag16 ? 2 : 4);
   int block = opt_block ? std::min(opt_block, 128) : 64;  // search_knn2_kernel is bounded at 128 threads per CTA
   while (block > 32 && (size_t)(block / 32) * per_warp > max_smem) block /= 2;
@@ -162,7 +183,13 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   if (smem > max_smem) return fail(HNSW_ERR_INVALID, "dimension too large for the staged search kernel");
   // rows of up to two cp.async instructions (32-d, 128-d) are copied with cp.async, longer ones with bulk-async copies
   const bool cp = opt_row_copy == 1 && (kind == kKindR4 || kind == kKindR1);
-  const int id = search2_id(S, tag16) + (cp ? kKernSearch2Cp - kKernSearch2 : 0);
+  int id = search2_id(S, tag16) + (cp ? kKernSearch2Cp - kKernSearch2 : 0);
+  uint32_t table_slots = slots;
+  if (opt_recent_ways == 2 && cp && tag16 && slots >= 128 && n_ids <= (1ull << (slot_bits - 1 + 15))) {
+    // DRAFT: the same bytes as `slots` 16-bit tags, organised as slots / 2 two-way sets (one 32-bit word per set)
+    table_slots = slots / 2;
+    id = kKernSearch2W2 + (S == 4 ? 0 : S == 8 ? 1 : S == 16 ? 2 : 3);
+  }
   int occ = occupancy(kind, id, efr, block, smem);
   if (occ < 1) return fail(HNSW_ERR_CUDA, "staged search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
@@ -184,7 +211,7 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   a.stats = d_stats;
   a.work_counter = ctl + 0;
   a.retry_count = ctl + 2;
-  a.vis_slots = slots;
+  a.vis_slots = table_slots;
   LaunchCfg c{grid, block, smem, s};
   e = run(kind, id, efr, c, g, &a);
   if (e != cudaSuccess) return cuda_fail(e, "search_knn2 launch");
@@ -299,7 +326,7 @@ int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uin
 int Index::search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
                              uint32_t* n_out) {
   const int efr = efr_for(ef);
-  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..512)", ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..1024)", ef);
   if (ep >= n_ids || h_level[ep] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", ep);
   const uint32_t slots = next_pow2(std::max<uint64_t>(65536, (uint64_t)ef * 512));
   int rc = ensure_scratch(s_vis, (size_t)slots * 4);

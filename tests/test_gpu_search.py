@@ -77,6 +77,67 @@ def test_latency_mode_parity(name, efs):
     dev.set_option("row_copy", 0)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,efs", [("cfg1_10k_d32_m5", (1, 16, 100)), ("d128_m16", (8, 64, 200, 512)), ("d768_m32", (16, 128))])
+def test_cta_latency_kernel_parity(name, efs):
+    """DRAFT (branch r2-cta-draft): option search_cta = 1 runs one query per CTA of 4 warps for small calls
+    (search_knn2_cta_kernel).  First thing to run on hardware next round — under a timeout: two named barriers per round."""
+    c = case(name)
+    dev = device_index(name)
+    dev.set_option("search_cta", 1)
+    for ef in efs:
+        for lo, n in ((0, 1), (1, 7), (8, 100)):
+            q = c["q"][lo:lo + n]
+            oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=ef)
+            ok = ost[:, 3] == 0
+            ids, sims, counts = dev.search_batch(q, 10, ef=ef)
+            assert np.array_equal(counts, ocounts)
+            assert np.array_equal(ids[ok], oids[ok])
+            assert np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
+    dev.set_option("search_cta", 0)
+
+
+@pytest.mark.parametrize("name", ["cfg1_10k_d32_m5", "d128_m16"])
+def test_two_way_visited_sets_parity(name):
+    """DRAFT (branch r2-cta-draft): option recent_ways = 2 (Recent<Way2>): same results, fewer or equal re-evaluations."""
+    c = case(name)
+    dev = device_index(name)
+    q = c["q"][:300]
+    oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=64)
+    ok = ost[:, 3] == 0
+    evals = {}
+    for ways in (1, 2):
+        dev.set_option("search_impl", 2)
+        dev.set_option("recent_ways", ways)
+        ids, sims, counts, st = dev.search_batch(q, 10, ef=64, stats=True)
+        assert np.array_equal(ids[ok], oids[ok]) and np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
+        assert np.array_equal(counts, ocounts)
+        assert np.array_equal(st[ok, 1:3].astype(np.uint64), ost[ok, 1:3]) and np.all(st[ok, 0] >= ost[ok, 0])
+        evals[ways] = int(st[ok, 0].sum())
+    dev.set_option("search_impl", 0)
+    dev.set_option("recent_ways", 1)
+    assert evals[2] <= evals[1] * 1.01
+
+
+def test_ef_up_to_1024():
+    """DRAFT (branch r2-cta-draft): a sixth list class (32 registers per lane x 2) lifts the ef / ef_construction limit
+    from 512 to 1024 — search parity at ef 600 / 1024 and an exact build with ef_construction = 700."""
+    import oracle
+    import redis_hnsw_b200 as r
+
+    c = case("d128_m16")
+    dev = device_index("d128_m16")
+    for ef in (600, 1024):
+        assert_search_parity(dev, c["oracle"], c["q"][:200], 10, ef)
+    n = 1500
+    orc = oracle.Oracle(c["dim"], c["m"], 700)
+    orc.add_batch(c["x"][:n], c["levels"][:n])
+    d2 = r.DeviceIndex(c["dim"], c["m"], 700)
+    d2.add_batch(c["x"][:n], c["levels"][:n], mode=r.BUILD_EXACT)
+    go, gd = orc.export_graph(), d2.export_graph()
+    assert np.array_equal(go["row_offs"], gd["row_offs"]) and np.array_equal(go["nbrs"], gd["nbrs"])
+
+
 def test_default_ef_is_ef_construction():
     """core.rs:485: search_knn always searches with ef = ef_construction."""
     c = case("cfg1_10k_d32_m5")
