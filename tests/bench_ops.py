@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--cpu-add", type=int, default=200)
     ap.add_argument("--cpu-del", type=int, default=100)
     ap.add_argument("--only", default="all", choices=["all", "search"])
+    ap.add_argument("--option", action="append", default=[], help="name=value library option set after the build")
     args = ap.parse_args()
     import oracle
     import redis_hnsw_b200 as r
@@ -54,6 +55,10 @@ def main():
     out = {"workload": wl, "n": n, "dim": dim, "M": m, "ef_construction": efc, "ef_search": args.ef,
            "fast_build_s": build_s}
 
+    for opt in args.option:
+        name, val = opt.split("=")
+        dev.set_option(name, int(val))
+    out["options"] = args.option
     orc = oracle.Oracle(dim, m, efc)
     orc.import_graph(x, dev.export_graph())
 

@@ -1,0 +1,279 @@
+// Design probe for the speculative-exact batched builder: how long are the dependency chains
+// between the inserts of a window?  CPU only, set semantics of core.rs:489-599 on tie-free data (the algorithm the
+// device kernels run: search -> top-m -> mirrored link -> re-selection of over-full rows).
+//
+// Every insert of a window is executed in stream order while its read set and write set are logged:
+//   reads   search rows (row, threshold at expansion time), re-selection sweep rows (row, e, cap-th sim), strict rows
+//           (rows whose whole content matters: read-modify-write targets, the re-selected row itself)
+//   writes  (row, ids added, ids removed)
+// Insert i depends on an earlier insert j of the window when a write of j meets a read of i
+//   coarse : on the same row
+//   fine   : ... and a changed id could enter the list the read fed (sim above the recorded threshold), or the read is strict
+// Output per window size B: inserts with at least one dependency, longest chain (= Jacobi sweeps needed), length of
+// the conflict-free prefix.
+//
+// usage: sim_spec_build vecs.bin n dim m efc seed checkpoints...      (vecs.bin = raw f32 [n][dim])
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <queue>
+#include <random>
+#include <unordered_map>
+#include <vector>
+
+static int DIM, M, EFC;
+static std::vector<float> V;
+static std::vector<int> LEVEL;
+static std::vector<std::vector<std::vector<uint32_t>>> NB;  // [node][level]
+static int max_layer = 0;
+static uint32_t entry = 0;
+
+static inline float sim(uint32_t a, uint32_t b) {
+  const float *x = &V[(size_t)a * DIM], *y = &V[(size_t)b * DIM];
+  float acc = 0;
+  for (int i = 0; i < DIM; ++i) {
+    float d = x[i] - y[i];
+    acc += d * d;
+  }
+  return -acc;
+}
+
+struct Read {
+  uint64_t row;
+  int kind;        // 0 strict, 1 search (query = the insert's node), 2 sweep (query = e)
+  uint32_t qnode;  // node whose vector the changed ids are compared with
+  float thr;       // -inf: list not full
+};
+struct Write {
+  uint64_t row;
+  std::vector<uint32_t> diff;
+};
+struct Log {
+  std::vector<Read> reads;
+  std::vector<Write> writes;
+};
+static Log* LOG = nullptr;
+static inline uint64_t key(uint32_t node, int lvl) { return ((uint64_t)lvl << 32) | node; }
+
+static std::vector<uint32_t> stamp;
+static uint32_t epoch = 0;
+
+typedef std::pair<float, uint32_t> P;
+
+static std::vector<P> search_level(uint32_t q, uint32_t ep, int ef, int lvl) {
+  ++epoch;
+  stamp[ep] = epoch;
+  std::priority_queue<P> c;                                      // nearest first
+  std::priority_queue<P, std::vector<P>, std::greater<P>> w;    // worst first
+  float s = sim(q, ep);
+  c.push({s, ep});
+  w.push({s, ep});
+  while (!c.empty()) {
+    P cp = c.top();
+    c.pop();
+    if (cp.first < w.top().first) break;
+    const auto& nb = NB[cp.second];
+    if ((int)nb.size() <= lvl) continue;
+    if (LOG) LOG->reads.push_back({key(cp.second, lvl), 1, q, (int)w.size() >= ef ? w.top().first : -INFINITY});
+    for (uint32_t n : nb[lvl]) {
+      if (stamp[n] == epoch) continue;
+      stamp[n] = epoch;
+      float e = sim(q, n);
+      if (e > w.top().first || (int)w.size() < ef) {
+        c.push({e, n});
+        w.push({e, n});
+        if ((int)w.size() > ef) w.pop();
+      }
+    }
+  }
+  std::vector<P> out;
+  while (!w.empty()) out.push_back(w.top()), w.pop();
+  std::reverse(out.begin(), out.end());
+  return out;
+}
+
+static void log_write(uint32_t node, int lvl, std::vector<uint32_t> diff) {
+  if (LOG) LOG->writes.push_back({key(node, lvl), std::move(diff)});
+}
+static void log_strict(uint32_t node, int lvl) {
+  if (LOG) LOG->reads.push_back({key(node, lvl), 0, 0, 0});
+}
+
+static void add_nb(uint32_t a, int lvl, uint32_t b) {
+  auto& l = NB[a][lvl];
+  if (std::find(l.begin(), l.end(), b) == l.end()) l.push_back(b), log_write(a, lvl, {b});
+}
+static void rm_nb(uint32_t a, int lvl, uint32_t b) {
+  auto& l = NB[a][lvl];
+  auto it = std::find(l.begin(), l.end(), b);
+  if (it != l.end()) l.erase(it), log_write(a, lvl, {b});
+}
+
+static uint64_t n_reprunes = 0;
+static uint64_t KH[8];
+
+static void reprune(uint32_t e, int lvl, int cap) {
+  std::vector<uint32_t> old = NB[e][lvl];
+  ++epoch;
+  stamp[e] = epoch;
+  std::vector<P> cand;
+  for (uint32_t n : old)
+    if (stamp[n] != epoch) stamp[n] = epoch, cand.push_back({sim(e, n), n});
+  size_t first_sweep_read = LOG ? LOG->reads.size() : 0;
+  for (uint32_t n : old) {
+    if (LOG) LOG->reads.push_back({key(n, lvl), 2, e, 0});
+    for (uint32_t x : NB[n][lvl])
+      if (stamp[x] != epoch) stamp[x] = epoch, cand.push_back({sim(e, x), x});
+  }
+  std::sort(cand.begin(), cand.end(), std::greater<P>());
+  if ((int)cand.size() > cap) cand.resize(cap);
+  float thr = (int)cand.size() >= cap ? cand.back().first : -INFINITY;
+  if (LOG)
+    for (size_t i = first_sweep_read; i < LOG->reads.size(); ++i) LOG->reads[i].thr = thr;
+  std::vector<uint32_t> sel;
+  for (auto& p : cand) sel.push_back(p.second);
+  std::vector<uint32_t> keep, add, rem;
+  for (uint32_t n : old) (std::find(sel.begin(), sel.end(), n) != sel.end() ? keep : rem).push_back(n);
+  for (uint32_t n : sel)
+    if (std::find(old.begin(), old.end(), n) == old.end()) add.push_back(n);
+  std::vector<uint32_t> nl = keep;
+  nl.insert(nl.end(), add.begin(), add.end());
+  NB[e][lvl] = nl;
+  std::vector<uint32_t> d = add;
+  d.insert(d.end(), rem.begin(), rem.end());
+  log_write(e, lvl, d);
+  for (uint32_t x : add) log_strict(x, lvl), add_nb(x, lvl, e);
+  for (uint32_t x : rem) log_strict(x, lvl), rm_nb(x, lvl, e);
+  ++n_reprunes;
+}
+
+static void insert(uint32_t q) {
+  int l = LEVEL[q];
+  NB[q].resize(l + 1);
+  int l_max = max_layer;
+  uint32_t ep = entry;
+  for (int lc = l_max; lc >= 0; --lc) {
+    bool link = lc <= l;
+    auto w = search_level(q, ep, link ? EFC : 1, lc);
+    ep = w[0].second;
+    if (!link) continue;
+    int cap = lc == 0 ? 2 * M : M;
+    size_t n_sel = std::min<size_t>(w.size(), M);
+    std::vector<uint32_t> sel;
+    for (size_t i = 0; i < n_sel; ++i) sel.push_back(w[i].second);
+    NB[q][lc] = sel;
+    log_write(q, lc, sel);
+    for (uint32_t r : sel) log_strict(r, lc), add_nb(r, lc, q);
+    for (uint32_t e : sel)
+      if ((int)NB[e][lc].size() > cap) reprune(e, lc, cap);
+  }
+  if (l > l_max) max_layer = l, entry = q;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 8) return 1;
+  const char* path = argv[1];
+  size_t n = atol(argv[2]);
+  DIM = atoi(argv[3]), M = atoi(argv[4]), EFC = atoi(argv[5]);
+  int seed = atoi(argv[6]);
+  std::vector<size_t> cps;
+  for (int i = 7; i < argc; ++i) cps.push_back(atol(argv[i]));
+  V.resize(n * DIM);
+  FILE* f = fopen(path, "rb");
+  if (!f || fread(V.data(), 4, n * DIM, f) != n * DIM) return 2;
+  fclose(f);
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(0, 1);
+  LEVEL.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    double u = U(rng);
+    if (u == 0) u = 1e-300;
+    LEVEL[i] = (int)std::floor(-std::log(u) / std::log((double)M));
+  }
+  LEVEL[0] = 0;
+  NB.resize(n);
+  stamp.assign(n, 0);
+  NB[0].resize(1);
+  const size_t WMAX = 2048;
+  size_t next = 1;
+  for (size_t cp : cps) {
+    for (; next < cp && next < n; ++next) insert((uint32_t)next);
+    if (next + WMAX > n) break;
+    // a window never contains a node that raises max_layer (it runs alone): skip those here
+    std::vector<Log> logs;
+    std::vector<uint32_t> ids;
+    uint64_t r0 = n_reprunes;
+    while (ids.size() < WMAX && next < n) {
+      if (LEVEL[next] > max_layer) {
+        insert((uint32_t)next++);
+        continue;
+      }
+      logs.emplace_back();
+      LOG = &logs.back();
+      insert((uint32_t)next);
+      LOG = nullptr;
+      ids.push_back((uint32_t)next++);
+    }
+    double avg_r = 0, avg_w = 0;
+    for (auto& L : logs) avg_r += L.reads.size(), avg_w += L.writes.size();
+    printf("N=%zu window=%zu reads/insert=%.1f writes/insert=%.1f reprunes/insert=%.2f\n", cp, ids.size(), avg_r / ids.size(),
+           avg_w / ids.size(), (double)(n_reprunes - r0) / ids.size());
+    for (int fine = 0; fine <= 1; ++fine)
+      for (size_t B : {16, 32, 64, 128, 256, 512, 1024, 2048}) {
+        // average over the disjoint windows of size B inside the logged stretch
+        double dep_frac = 0, depth_sum = 0, prefix_sum = 0, sweeps_cost = 0;
+        size_t nw = ids.size() / B;
+        for (size_t wdx = 0; wdx < nw; ++wdx) {
+          std::unordered_map<uint64_t, std::vector<std::pair<int, const Write*>>> wr;
+          std::vector<int> depth(B, 0);
+          size_t n_dep = 0, prefix = B;
+          int maxd = 0;
+          for (size_t i = 0; i < B; ++i) {
+            const Log& L = logs[wdx * B + i];
+            int d = 0;
+            for (const Read& r : L.reads) {
+              auto it = wr.find(r.row);
+              if (it == wr.end()) continue;
+              for (auto& jw : it->second) {
+                bool hit = true;
+                if (fine && r.kind != 0) {
+                  hit = false;
+                  if (r.thr == -INFINITY) hit = true;
+                  else
+                    for (uint32_t z : jw.second->diff)
+                      if (z != r.qnode && sim(r.qnode, z) > r.thr) hit = true;
+                }
+                if (hit) d = std::max(d, depth[jw.first] + 1);
+                if (hit && fine && B == 64) KH[r.kind + (r.kind == 1 && r.thr == -INFINITY ? 2 : 0) + ((r.row >> 32) ? 4 : 0)]++;
+              }
+            }
+            depth[i] = d;
+            if (d > 0) {
+              ++n_dep;
+              if (prefix == B) prefix = i;
+            }
+            maxd = std::max(maxd, d);
+            for (const Write& w : L.writes) wr[w.row].push_back({(int)i, &w});
+          }
+          dep_frac += (double)n_dep / B;
+          depth_sum += maxd + 1;
+          prefix_sum += prefix;
+          // executions if every insert at chain depth d runs d+1 times (upper bound of the Jacobi re-executions)
+          double ex = 0;
+          for (size_t i = 0; i < B; ++i) ex += depth[i] + 1;
+          sweeps_cost += ex / B;
+        }
+        if (nw)
+          printf("  %s B=%4zu  dependent=%.3f  sweeps=%.2f  inserts/sweep=%.1f  prefix=%.1f  exec/insert<=%.2f\n", fine ? "fine  " : "coarse", B,
+                 dep_frac / nw, depth_sum / nw, B / (depth_sum / nw), prefix_sum / nw, sweeps_cost / nw);
+      }
+    printf("  fine hits at B=64 by kind: L0 strict=%llu search=%llu sweep=%llu search-notfull=%llu | upper strict=%llu search=%llu sweep=%llu notfull=%llu\n",
+           (unsigned long long)KH[0], (unsigned long long)KH[1], (unsigned long long)KH[2], (unsigned long long)KH[3], (unsigned long long)KH[4],
+           (unsigned long long)KH[5], (unsigned long long)KH[6], (unsigned long long)KH[7]);
+    for (auto& k : KH) k = 0;
+    fflush(stdout);
+  }
+  return 0;
+}
