@@ -49,8 +49,11 @@ enum {
 /* Build modes for hnsw_index_add_batch. */
 enum {
   HNSW_BUILD_EXACT = 0, /* sequentially consistent: same graph as inserting one node at a time (reference semantics) */
-  HNSW_BUILD_FAST = 1   /* batched snapshot inserts: same per-insert algorithm, searches of one batch do not see
+  HNSW_BUILD_FAST = 1,  /* batched snapshot inserts: same per-insert algorithm, searches of one batch do not see
                            each other's edges; graph differs from the sequential one (recall-equivalent) */
+  HNSW_BUILD_SPEC = 2   /* speculative-exact: windows of inserts run in parallel against the committed graph and commit
+                           strictly in stream order, each only if no row it read was written since; the graph is the
+                           sequential one (identical to HNSW_BUILD_EXACT and to the reference, core.rs:489-599) */
 };
 
 /* The pub fields of Index the reference's host code reads (core.rs:303-319; types.rs:62-91). */
@@ -101,7 +104,7 @@ int hnsw_index_add(hnsw_index_t* idx, const float* data, uint64_t n, int32_t lev
 
 /* A NODE.ADD stream of `count` vectors ([count][data_dim], row-major host memory).  `levels` may be NULL
  * (draw all) or hold one entry per vector (-1 = draw).  Ids first_id .. first_id+count-1 are assigned in order.
- * mode: HNSW_BUILD_EXACT or HNSW_BUILD_FAST. */
+ * mode: HNSW_BUILD_EXACT, HNSW_BUILD_FAST or HNSW_BUILD_SPEC. */
 int hnsw_index_add_batch(hnsw_index_t* idx, uint64_t count, const float* data, const int32_t* levels, int mode,
                          uint32_t* first_id);
 
@@ -192,6 +195,13 @@ uint64_t hnsw_launch_count(void);
 /* Builder counters of the last add_batch: [0] inserts, [1] speculative conflicts re-run, [2] re-prunes,
  * [3] distance evaluations. */
 int hnsw_index_build_stats(hnsw_index_t* idx, uint64_t* out4);
+/* All builder counters since the index was created.  Writes up to `cap` values and stores how many exist in *n:
+ * [0] inserts  [1] speculative executions thrown away (SPEC) / rows not re-selected (FAST)  [2] re-prunes
+ * [3] distance evaluations  [4] FAST: over-full rows that did not fit the re-prune worklist  [5] FAST: re-prunes skipped
+ * [6] FAST: edges refused because a hub row was full  [7] SPEC: commit rounds  [8] SPEC: executions (first + repeated)
+ * [9] SPEC: distance evaluations of thrown-away executions  [10] SPEC: inserts sent to the one-warp EXACT kernel
+ * [11] SPEC: largest window. */
+int hnsw_index_build_stats_ex(hnsw_index_t* idx, uint64_t* out, uint32_t cap, uint32_t* n);
 
 const char* hnsw_last_error(void);
 const char* hnsw_version(void);

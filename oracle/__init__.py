@@ -39,6 +39,11 @@ def lib():
             f.restype = C.c_float
             f.argtypes = [fp, fp, C.c_uint64]
         L.orc_euclidean_batch.argtypes = [fp, fp, C.c_uint64, C.c_uint64, fp]
+        L.orc_cut_ties.restype = C.c_uint64
+        L.orc_cut_ties.argtypes = []
+        L.orc_cut_ties_reset.argtypes = []
+        L.orc_evict_ties.restype = C.c_uint64
+        L.orc_evict_ties.argtypes = []
         L.orc_level_from_u.restype = C.c_int
         L.orc_level_from_u.argtypes = [C.c_double, C.c_int]
         L.orc_add.restype = C.c_int64
@@ -103,6 +108,16 @@ def euclidean_batch(a, b):
     out = np.empty(a.shape[0], dtype=np.float32)
     lib().orc_euclidean_batch(_p(a, C.c_float), _p(b, C.c_float), a.shape[0], a.shape[1], _p(out, C.c_float))
     return out
+
+
+def cut_ties(reset=False):
+    """(select ties, eviction ties) since the last reset (process-wide): equal sims of different nodes on either side of a
+    cut — the m-th / (m+1)-th candidate of select_neighbors, the two worst of w at an eviction — i.e. outcomes the reference
+    leaves to BinaryHeap internals.  Parity fixtures are chosen so that the first is 0."""
+    n = (int(lib().orc_cut_ties()), int(lib().orc_evict_ties()))
+    if reset:
+        lib().orc_cut_ties_reset()
+    return n
 
 
 def level_from_u(u, m):

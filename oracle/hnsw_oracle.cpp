@@ -61,6 +61,14 @@ struct Stats {
 
 thread_local Stats* g_stats = nullptr;
 
+// Ties that can change a RESULT (not just an order): two different nodes with the same sim on either side of a cut —
+// the m-th / (m+1)-th candidate of select_neighbors, or the two worst members of `w` at an eviction in search_level.
+// There the reference's outcome is decided by BinaryHeap internals; parity fixtures are chosen so that this stays 0
+// (tests/golden/make_graph_fingerprint.py).  Diagnostic only: no behaviour depends on it.
+std::atomic<uint64_t> g_cut_ties{0};     // select_neighbors: m-th and (m+1)-th candidate tie
+std::atomic<uint64_t> g_evict_ties{0};   // search_level: the two worst members of w tie at an eviction (almost always harmless:
+                                         // both sit at the far edge of an early, wide w and are evicted shortly after)
+
 // ---------------------------------------------------------------- metric (metrics.rs)
 
 // metrics.rs:79-84 — strict left fold, mul and add rounded separately (no contraction).
@@ -358,7 +366,13 @@ struct Oracle {
           if (adm > 0 || w.len() < ef) {         // :657
             c.push({e, nb});                     // :659
             w.push({e, nb});                     // :660
-            if (w.len() > ef) w.pop();           // :662-664
+            if (w.len() > ef) {                  // :662-664
+              Pair gone = w.pop();
+              if (of_cmp(gone.sim, w.peek().sim) == 0 && gone.id != w.peek().id) {
+                g_evict_ties++;
+                if (getenv("ORC_TIE_DEBUG")) fprintf(stderr, "evict tie: ef=%zu lvl=%d gone=%u kept=%u sim=%g\n", ef, lvl, gone.id, w.peek().id, gone.sim);
+              }
+            }
           }
         }
       }
@@ -404,6 +418,18 @@ struct Oracle {
       Pair p = wd.pop();
       if (p.id == query || (ignored != NONE && p.id == ignored)) continue;
       r.push(p);                                       // :752
+    }
+    if (r.len() == mm && mm > 0) {                     // diagnostic: a tie across the cut (see g_cut_ties)
+      float worst = r.data[0].sim;
+      for (const Pair& p : r.data) worst = std::min(worst, p.sim);
+      bool tie = false;
+      for (const MaxHeap* rest : {&wd, &w})
+        for (const Pair& p : rest->data)
+          if (p.id != query && p.id != ignored && of_cmp(p.sim, worst) == 0) tie = true;
+      if (tie) {
+        g_cut_ties++;
+        if (getenv("ORC_TIE_DEBUG")) fprintf(stderr, "select tie: query=%u mm=%zu lc=%d worst=%g |w|=%zu |wd|=%zu\n", query, mm, lc, worst, w.len(), wd.len());
+      }
     }
     return r;
   }
@@ -609,6 +635,10 @@ int orc_have_avx2() { return g_have_avx2 ? 1 : 0; }
 void orc_euclidean_batch(const float* a, const float* b, uint64_t n, uint64_t dim, float* out) {
   for (uint64_t i = 0; i < n; ++i) out[i] = euclidean(a + i * dim, b + i * dim, (size_t)dim);
 }
+
+uint64_t orc_cut_ties() { return g_cut_ties.load(); }
+uint64_t orc_evict_ties() { return g_evict_ties.load(); }
+void orc_cut_ties_reset() { g_cut_ties = 0, g_evict_ties = 0; }
 
 int orc_level_from_u(double u, int m) { return Oracle::level_from_u(u, 1.0 / std::log((double)m)); }
 

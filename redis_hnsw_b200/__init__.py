@@ -5,5 +5,5 @@ this package only holds the host-side mirror of the reference's `Index` interfac
 the ctypes binding.  Importing never touches the GPU; creating an index does, and fails loudly without one.
 """
 from . import data, sharding  # noqa: F401
-from ._lib import BUILD_EXACT, BUILD_FAST, REDIS_MODULE_PATH, SO_PATH, build  # noqa: F401
+from ._lib import BUILD_EXACT, BUILD_FAST, BUILD_SPEC, REDIS_MODULE_PATH, SO_PATH, build  # noqa: F401
 from .index import DeviceIndex, HNSWError, Index, SearchResult, l2_batch, launch_count  # noqa: F401

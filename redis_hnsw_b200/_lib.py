@@ -11,7 +11,7 @@ REDIS_MODULE_PATH = os.path.join(_HERE, "libredis_hnsw_b200.so")  # redis-server
 HNSW_OK = 0
 ERR_DIM_MISMATCH, ERR_EXISTS, ERR_NOT_FOUND, ERR_INVALID, ERR_CUDA, ERR_OOM = 1, 2, 3, 4, 5, 6
 NO_NODE = 0xFFFFFFFF
-BUILD_EXACT, BUILD_FAST = 0, 1
+BUILD_EXACT, BUILD_FAST, BUILD_SPEC = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -56,6 +56,7 @@ SYMBOLS = {
     "hnsw_index_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "hnsw_launch_count": (C.c_uint64, []),
     "hnsw_index_build_stats": (C.c_int, [_vp, _u64p]),
+    "hnsw_index_build_stats_ex": (C.c_int, [_vp, _u64p, C.c_uint32, _u32p]),
     "hnsw_last_error": (C.c_char_p, []),
     "hnsw_version": (C.c_char_p, []),
 }

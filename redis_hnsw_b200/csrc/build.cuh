@@ -41,6 +41,7 @@ enum BuildCtl : int {
   kCtlSkipped = 10,     // re-prunes skipped (list too long / visited overflow)
   kCtlProgress = 11,    // EXACT: inserts completed
   kCtlTouched = 12,     // EXACT: entries written to the touched buffer
+  kCtlRefused = 13,     // FAST: edges dropped on both sides because a hub row already held `lcap` ids
   kCtlWords = 32,
 };
 
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(256) build_link_kernel(Graph g, FastArgs a) {
       uint32_t len = row_append_unique(g, r, lc, q, edit, a.lcap, lane, &full);
       if (full) {
         refused = true;
-        if (lane == 0) a.sel_ids[(size_t)t * a.m + i] = kEmpty;
+        if (lane == 0) a.sel_ids[(size_t)t * a.m + i] = kEmpty, atomicAdd(a.ctl + kCtlRefused, 1u);
       }
       if (len != kEmpty && len > cap && lane == 0) {
         uint32_t* st = (key & 0x80000000u) ? a.stampU + (key & 0x7FFFFFFFu) : a.stamp0 + key;
@@ -868,6 +869,7 @@ __global__ void __launch_bounds__(256) build_apply_kernel(Graph g, FastArgs a) {
       row_append_unique(g, x, lc, e, edit, a.lcap, lane, &full);
       row_unlock(lk, lane);
       if (full) {  // x is a hub whose list is full: drop the edge on e's side too (keeps the graph symmetric)
+        if (lane == 0) atomicAdd(a.ctl + kCtlRefused, 1u);
         row_lock(elock, lane);
         row_remove(g, e, lc, x, edit, a.lcap, lane);
         row_unlock(elock, lane);

@@ -9,6 +9,7 @@
 
 #include "../../include/hnsw_b200.h"
 #include "index.hpp"
+#include "spec_launch.cuh"
 
 namespace hnsw {
 
@@ -53,7 +54,10 @@ int Index::set_entry(int32_t entry_, int32_t max_layer_) {
 static uint32_t list_capacity(uint32_t W) { return std::max<uint32_t>(512, 16 * W); }
 
 // list registers: the candidate list must hold ef_construction entries (search) and m_max_0 entries (re-selection)
-static int build_efr(const Index& ix) { return std::max(efr_for(ix.ef_construction), efr_for(ix.m_max_0)); }
+static int build_efr(const Index& ix) {
+  const int a = efr_for(ix.ef_construction), b = efr_for(ix.m_max_0);
+  return (a && b) ? std::max(a, b) : 0;  // 0: one of the two does not fit a list class (m_max_0 > 1024 must fail loudly)
+}
 
 // ---------------------------------------------------------------- EXACT
 
@@ -368,6 +372,9 @@ int Index::fast_batch(uint32_t first, uint32_t count) {
   if ((rc = pull_meta())) return rc;
   build_stats[0] += count;
   build_stats[1] += h[kCtlWlDropped] + h[kCtlSkipped];
+  build_stats_ex[4 - 4] += h[kCtlWlDropped];
+  build_stats_ex[5 - 4] += h[kCtlSkipped];
+  build_stats_ex[6 - 4] += h[kCtlRefused];
   build_stats[2] += h[kCtlReprunes];
   build_stats[3] += h[kCtlDistEvals];
   tr.mark(5);
@@ -410,6 +417,142 @@ int Index::add_fast(uint32_t first, uint32_t count) {
     node_count += B;
     if (solo_top && (rc = set_entry((int32_t)(first + pos), h_level[first + pos]))) return rc;
     pos += B;
+  }
+  return HNSW_OK;
+}
+
+
+// ---------------------------------------------------------------- SPEC (spec.cuh)
+
+static cudaError_t run_spec(int kind, int efr, bool small, const LaunchCfg& c, const Graph& g, const SpecArgs& a, bool occ_only,
+                            int* occ) {
+  switch (kind) {
+    case kKindR1: return run_spec_r1(efr, small, c, g, a, occ_only, occ);
+    case kKindR4: return run_spec_r4(efr, small, c, g, a, occ_only, occ);
+    case kKindR24: return run_spec_r24(efr, small, c, g, a, occ_only, occ);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Speculative-exact NODE.ADD stream: ids first .. first+count-1, committed strictly in order (see spec.cuh).
+int Index::add_spec(uint32_t first, uint32_t count) {
+  if (count == 0) return HNSW_OK;
+  const int efr = build_efr(*this);
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
+  const uint32_t lcap = list_capacity(g.W);
+  const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
+  const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
+  const uint32_t vis_slots = 8192, wmaxe = 256, rcap = 2048, wcap = 8192, ring = 1024;
+  const size_t list_words = (size_t)((m + 31) & ~31u) + 5 * (size_t)lcap + g.W + 2 * (size_t)wmaxe;
+  const size_t smem = warp2_smem_bytes(dim, S, vis_slots, 4) + list_words * 4;
+  const bool small = m_max_0 <= 64;
+  int occ = 0;
+  if (staged_kind && smem <= max_smem) {
+    LaunchCfg c0{1, 32, smem, stream};
+    SpecArgs a0{};
+    run_spec(kind, efr, small, c0, g, a0, true, &occ);
+  }
+  if (occ < 1) {  // dimensions without a staged kernel (or lists too long for shared memory): the one-warp EXACT stream
+    int rc = add_exact(first, count, false);
+    if (!rc) node_count += count;
+    return rc;
+  }
+  const uint32_t resident = (uint32_t)std::min<uint64_t>(ring, (uint64_t)occ * num_sms);
+
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_ctl = 0, o_hdr = al(kSpecCtlWords * 4), o_rd = o_hdr + al((size_t)ring * kSpecHdrWords * 4),
+               o_wkey = o_rd + al((size_t)ring * rcap * 4), o_woff = o_wkey + al((size_t)ring * wmaxe * 4),
+               o_wdata = o_woff + al((size_t)ring * wmaxe * 4), total = o_wdata + al((size_t)ring * wcap * 4);
+  int rc = ensure_scratch(s_spec, total);
+  if (rc) return rc;
+  char* base = (char*)s_spec.p;
+  cudaError_t e = cudaMemsetAsync(base, 0, o_rd, stream);  // control words + slot headers
+  if (e != cudaSuccess) return cuda_fail(e, "spec memset");
+  SpecArgs a{};
+  a.ring = ring;
+  a.m = m, a.cap0 = m_max_0, a.capU = m_max, a.efc = ef_construction, a.lcap = lcap, a.vis_slots = vis_slots;
+  a.rcap = rcap, a.wcap = wcap, a.wmaxe = wmaxe;
+  a.ctl = (uint32_t*)(base + o_ctl);
+  a.hdr = (uint32_t*)(base + o_hdr);
+  a.rd = (uint32_t*)(base + o_rd);
+  a.wkey = (uint32_t*)(base + o_wkey);
+  a.woff = (uint32_t*)(base + o_woff);
+  a.wdata = (uint32_t*)(base + o_wdata);
+
+  uint32_t f = first;
+  const uint32_t end = first + count;
+  double ema = 4.0;  // committed inserts per round
+  uint32_t h[kSpecCtlWords];
+  uint32_t prev_exec = 0, prev_dist = 0, prev_repr = 0, prev_waste = 0;
+  const bool trace = std::getenv("HNSW_BUILD_TRACE") != nullptr;
+  while (f < end) {
+    uint32_t B = opt_spec_window ? opt_spec_window : (uint32_t)std::max(8.0, 4.0 * ema);
+    B = std::min(std::min(B, resident), end - f);
+    // a node that raises max_layer becomes the enterpoint of everything after it (core.rs:587-593): the window ends there
+    uint32_t wend = f + B;
+    for (uint32_t q = f; q < wend; ++q)
+      if (h_level[q] > max_layer) {
+        wend = q + 1;
+        break;
+      }
+    B = wend - f;
+    if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)B * 64 + 4096))) return rc;
+    a.frontier = f;
+    a.count = B;
+    a.ver0 = d_ver0;
+    a.verU = d_verU;
+    LaunchCfg c1{(int)B, 32, smem, stream};
+    g_launches++;
+    e = run_spec(kind, efr, small, c1, g, a, false, nullptr);
+    if (e != cudaSuccess) return cuda_fail(e, "spec_exec launch");
+    g_launches++;
+    spec_commit_kernel<<<1, 256, 0, stream>>>(g, a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "spec_commit launch");
+    e = cudaMemcpyAsync(h, a.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return cuda_fail(e, "spec round");
+    const uint32_t committed = h[kSpecCommitted], reason = h[kSpecReason];
+    pool_used = h[kSpecPoolUsed];
+    max_layer = (int32_t)h[kSpecMaxLayer];
+    entry = (int32_t)h[kSpecEntry];
+    device_error = (int32_t)h[kSpecError];
+    build_stats[0] += committed;
+    // executions that were thrown away = executions - commits (a running balance: a round can commit inserts executed earlier)
+    build_stats[1] = (uint64_t)((int64_t)build_stats[1] + (int64_t)(h[kSpecExecuted] - prev_exec) - (int64_t)committed);
+    build_stats[2] += h[kSpecReprunesDone] - prev_repr;
+    build_stats[3] += h[kSpecDistEvals] - prev_dist;
+    build_stats_ex[7 - 4] += 1;
+    build_stats_ex[8 - 4] += h[kSpecExecuted] - prev_exec;
+    build_stats_ex[9 - 4] += h[kSpecDistWasted] - prev_waste;
+    build_stats_ex[11 - 4] = std::max<uint64_t>(build_stats_ex[11 - 4], B);
+    prev_exec = h[kSpecExecuted], prev_dist = h[kSpecDistEvals], prev_repr = h[kSpecReprunesDone], prev_waste = h[kSpecDistWasted];
+    if (trace && (build_stats_ex[7 - 4] % 256) == 1)
+      std::fprintf(stderr, "[spec] f=%u window=%u committed=%u reason=%u ema=%.1f\n", f, B, committed, reason, ema);
+    f += committed;
+    node_count += committed;
+    ema = 0.8 * ema + 0.2 * committed;
+    if (device_error) {
+      int err = device_error;
+      device_error = 0;
+      push_meta();
+      return fail(HNSW_ERR_INVALID, "speculative insert stopped at node %u (device error flags 0x%x: %s)", f, err,
+                  (err & kErrPoolExhausted) ? "overflow-row pool exhausted" : "adjacency list too long");
+    }
+    if (reason == 2) {  // the head insert's write log overflowed (a very large re-selection): it goes through the EXACT kernel
+      if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)(m_max_0 + 8) * 2 + 4096))) return rc;
+      if ((rc = add_exact(f, 1, false))) return rc;
+      node_count += 1;
+      f += 1;
+      build_stats_ex[10 - 4] += 1;
+      // the EXACT kernel does not stamp the rows it writes: every kept log is void
+      e = cudaMemsetAsync(a.hdr, 0, (size_t)ring * kSpecHdrWords * 4, stream);
+      if (e != cudaSuccess) return cuda_fail(e, "spec header reset");
+    } else if (reason == 4) {
+      if ((rc = ensure_pool((uint64_t)g.pool_cap * 2))) return rc;
+    } else if (committed == 0) {
+      return fail(HNSW_ERR_CUDA, "speculative builder made no progress at node %u (reason %u)", f, reason);
+    }
   }
   return HNSW_OK;
 }
@@ -506,7 +649,7 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
                      bool want_touched) {
   if (count == 0) return HNSW_OK;
   if (!data) return fail(HNSW_ERR_INVALID, "null data");
-  if (mode != HNSW_BUILD_EXACT && mode != HNSW_BUILD_FAST) return fail(HNSW_ERR_INVALID, "unknown build mode %d", mode);
+  if (mode != HNSW_BUILD_EXACT && mode != HNSW_BUILD_FAST && mode != HNSW_BUILD_SPEC) return fail(HNSW_ERR_INVALID, "unknown build mode %d", mode);
   if (n_ids + count >= 0x7FFFFFFFull) return fail(HNSW_ERR_INVALID, "too many nodes");
   if (!build_efr(*this)) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
   int rc = pull_meta();  // the device owns pool_used
@@ -557,6 +700,7 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
     if (!rc) node_count += rest;
     return rc;
   }
+  if (mode == HNSW_BUILD_SPEC) return add_spec(first + start, rest);
   return add_fast(first + start, rest);
 }
 
@@ -593,6 +737,13 @@ int hnsw_index_delete(hnsw_index_t* idx, uint32_t id) {
 int hnsw_index_build_stats(hnsw_index_t* idx, uint64_t* out4) {
   IDX_OR_FAIL(idx)
   for (int i = 0; i < 4; ++i) out4[i] = ix.build_stats[i];
+  return HNSW_OK;
+}
+
+int hnsw_index_build_stats_ex(hnsw_index_t* idx, uint64_t* out, uint32_t cap, uint32_t* n) {
+  IDX_OR_FAIL(idx)
+  if (n) *n = 12;
+  for (uint32_t i = 0; i < 12 && i < cap; ++i) out[i] = i < 4 ? ix.build_stats[i] : ix.build_stats_ex[i - 4];
   return HNSW_OK;
 }
 

@@ -122,6 +122,7 @@ int Index::ensure_nodes(uint64_t n) {
   GROW(g.upper_base, 4, 0xFF)
   GROW(g.level, 4, 0xFF)
   GROW(d_stamp0, 4, 0)
+  GROW(d_ver0, 4, 0)
 #undef GROW
   cap_nodes = nc;
   return HNSW_OK;
@@ -136,6 +137,8 @@ int Index::ensure_upper(uint64_t rows) {
   if (e != cudaSuccess) return cuda_fail(e, "grow ovfU");
   e = grow_buf((void**)&d_stampU, (size_t)cap_upper * 4, (size_t)nc * 4, 0, stream);
   if (e != cudaSuccess) return cuda_fail(e, "grow stampU");
+  e = grow_buf((void**)&d_verU, (size_t)cap_upper * 4, (size_t)nc * 4, 0, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "grow verU");
   cap_upper = nc;
   return HNSW_OK;
 }
@@ -191,7 +194,7 @@ int Index::pull_meta() {
 Index::~Index() {
   if (cudaSetDevice(device) != cudaSuccess) return;
   void* ptrs[] = {g.vecs, g.adj0, g.ovf0, g.upper_base, g.level, g.adjU, g.ovfU, g.pool, g.meta, g.locks,
-                  d_stamp0, d_stampU, s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p, s_bvis.p};
+                  d_stamp0, d_stampU, d_ver0, d_verU, s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p, s_bvis.p, s_spec.p};
   if (h_retry_seen) cudaFreeHost(h_retry_seen);
   if (h_stage) cudaFreeHost(h_stage);
   for (void* p : ptrs)
@@ -307,6 +310,8 @@ int Index::load_graph(uint64_t n, const float* vectors, const int32_t* levels, c
   if (e == cudaSuccess) e = cudaMemsetAsync(g.adjU, 0xFF, (size_t)cap_upper * W * 4, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(g.ovfU, 0xFF, (size_t)cap_upper * 4, stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(g.pool, 0xFF, (size_t)g.pool_cap * 32 * 4, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_ver0, 0, (size_t)cap_nodes * 4, stream);   // ids restart: stamps of the old graph are void
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_verU, 0, (size_t)cap_upper * 4, stream);
 #define UP(dst, vec, cnt)                                                                                 \
   if (e == cudaSuccess && (cnt) != 0)                                                                     \
     e = cudaMemcpyAsync(dst, vec.data(), (size_t)(cnt) * sizeof(vec[0]), cudaMemcpyHostToDevice, stream);
@@ -653,6 +658,9 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
   } else if (n == "build_batch") {
     if (value < 1) return fail(HNSW_ERR_INVALID, "build_batch must be >= 1");
     ix.opt_build_batch = (uint32_t)value;
+  } else if (n == "spec_window") {
+    if (value < 0 || value > 1024) return fail(HNSW_ERR_INVALID, "spec_window must be 0 (adaptive) .. 1024");
+    ix.opt_spec_window = (uint32_t)value;
   } else if (n == "build_impl") {
     if (value < 0 || value > 2) return fail(HNSW_ERR_INVALID, "build_impl must be 0 (auto), 1 (register-staged) or 2 (TMA-staged)");
     ix.opt_build_impl = (int)value;

@@ -47,6 +47,9 @@ struct Index {
   std::vector<uint32_t> touched;
   uint64_t rng_state = 0x9E3779B97F4A7C15ull;
   uint64_t build_stats[4] = {0, 0, 0, 0};
+  // [4] wl dropped [5] re-prunes skipped [6] edges refused [7] spec rounds [8] spec executions [9] spec wasted evals
+  // [10] spec exact fallbacks [11] spec largest window   (hnsw_index_build_stats_ex)
+  uint64_t build_stats_ex[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   // options / adaptive state
   uint32_t opt_vis_slots = 0;
@@ -69,9 +72,12 @@ struct Index {
   uint32_t epoch = 0;
   uint32_t build_hint = 0;        // largest batch the running add_batch call will reach (scratch is sized once)
   uint32_t exact_vis_slots = 0;
+  uint32_t* d_ver0 = nullptr;     // [cap_nodes] SPEC builder row stamps: 1 + id of the last insert that wrote the row
+  uint32_t* d_verU = nullptr;     // [cap_upper]
+  uint32_t opt_spec_window = 0;   // SPEC: fixed window size (0 = adaptive)
 
   // scratch
-  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis;
+  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis, s_spec;
 
   ~Index();
   int use_device();
@@ -112,6 +118,7 @@ struct Index {
   int delete_node(uint32_t id);
   bool exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) const;
   int add_fast(uint32_t first, uint32_t count);
+  int add_spec(uint32_t first, uint32_t count);
   int fast_batch(uint32_t first, uint32_t count);
   int set_entry(int32_t entry, int32_t max_layer);
   int draw_level();

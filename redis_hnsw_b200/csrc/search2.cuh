@@ -385,10 +385,15 @@ __device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S, T>& w,
   eval_and_admit<EFR, C, S, T, COPY>(g, w, nb, newmask, ef, L, adj_prefetch, lane);
 }
 
+// observer of the rows a search expands (the SPEC builder logs them as its read set, spec.cuh); the default does nothing
+struct NoSearchHook {
+  __device__ __forceinline__ void expand(uint32_t, uint32_t) const {}
+};
+
 // core.rs:607-675
-template <int EFR, int C, int S, class T, int COPY = 0>
+template <int EFR, int C, int S, class T, int COPY = 0, class Hook = NoSearchHook>
 __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w, uint32_t ep, int ef, uint32_t level,
-                                              CandList<EFR>& L, Counters& cnt, int lane) {
+                                              CandList<EFR>& L, Counters& cnt, int lane, const Hook& hook = Hook()) {
   w.seen.clear(lane);
   L.init();
   const uint32_t* adj_prefetch = (level == 0 && ef > 1) ? g.adj0 : nullptr;
@@ -408,6 +413,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
     uint32_t* ovf;
     const uint32_t* row = row_ptr(g, cid, level, &ovf);          // core.rs:642-645
     if (!row) continue;
+    hook.expand(cid, level);
     bool more = true;
     for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
       const uint32_t nb = row[c * 32 + lane];

@@ -44,6 +44,10 @@ enum SpecCtl : int {
   kSpecDistEvals = 3,  // distance evaluations of committed inserts (accumulates)
   kSpecReprunesDone = 4,
   kSpecDistWasted = 5, // distance evaluations of executions that were thrown away
+  kSpecPoolUsed = 6,   // copies of the index scalars after the commit walk (one transfer per round)
+  kSpecMaxLayer = 7,
+  kSpecEntry = 8,
+  kSpecError = 9,
   kSpecCtlWords = 16,
 };
 
@@ -97,10 +101,12 @@ struct SpecLog {
 
 // hook of search_layer2: every expanded row is a read (core.rs:642-646)
 struct SpecSearchHook {
-  const Graph* g;
+  const uint32_t* upper_base;
   SpecLog* lg;
   int lane;
-  __device__ __forceinline__ void expand(uint32_t node, uint32_t level) const { lg->read(row_key(*g, node, level), lane); }
+  __device__ __forceinline__ void expand(uint32_t node, uint32_t level) const {
+    lg->read(level == 0 ? node : (0x80000000u | (upper_base[node] + level - 1)), lane);   // row_key()
+  }
 };
 
 // the insert's view of the adjacency list of (node, level): its own latest version, else the graph's (logged as a read)
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   lg.woff_s = lg.wkey_s + a.wmaxe;
   lg.rcap = a.rcap, lg.wcap = a.wcap, lg.wmaxe = a.wmaxe;
   lg.n_reads = lg.n_entries = lg.used = lg.flags = 0;
-  SpecSearchHook hook{&g, &lg, lane};
+  SpecSearchHook hook{g.upper_base, &lg, lane};
 
   CandList<EFR> L;
   CandList<ER> R;
@@ -425,6 +431,10 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
     a.ctl[kSpecReason] = reason;
     a.ctl[kSpecDistEvals] += dist;
     a.ctl[kSpecReprunesDone] += reprunes;
+    a.ctl[kSpecPoolUsed] = (uint32_t)g.meta[kMetaPoolUsed];
+    a.ctl[kSpecMaxLayer] = (uint32_t)g.meta[kMetaMaxLayer];
+    a.ctl[kSpecEntry] = (uint32_t)g.meta[kMetaEntry];
+    a.ctl[kSpecError] = (uint32_t)g.meta[kMetaError];
   }
 }
 

@@ -126,7 +126,14 @@ class DeviceIndex:
     def build_stats(self):
         out = np.zeros(4, np.uint64)
         _check(self._L.hnsw_index_build_stats(self._h, _p(out, C.c_uint64)))
-        return dict(inserts=int(out[0]), conflicts=int(out[1]), reprunes=int(out[2]), dist_evals=int(out[3]))
+        d = dict(inserts=int(out[0]), conflicts=int(out[1]), reprunes=int(out[2]), dist_evals=int(out[3]))
+        ex = np.zeros(16, np.uint64)
+        n = C.c_uint32()
+        _check(self._L.hnsw_index_build_stats_ex(self._h, _p(ex, C.c_uint64), ex.size, C.byref(n)))
+        names = ("fast_worklist_dropped", "fast_reprunes_skipped", "fast_edges_refused", "spec_rounds", "spec_executions",
+                 "spec_dist_evals_wasted", "spec_exact_fallbacks", "spec_max_window")
+        d.update({k: int(ex[4 + i]) for i, k in enumerate(names)})
+        return d
 
     # -- search
     def search(self, q, k, ef=0):

@@ -1,0 +1,74 @@
+#!/usr/bin/env python
+"""Golden fingerprint of the ORACLE-built graph for 100 000 x 128-d, M=16, ef_construction=200 (BASELINE configs[1]
+parameters at a size the CPU oracle builds in minutes): the device builders claim list-for-list identity with the
+reference's sequential NODE.ADD stream (core.rs:489-599), and at this size the oracle is too slow to be rebuilt inside a
+GPU test, so its graph is pinned here once.
+
+    python tests/golden/make_graph_fingerprint.py        # ~6 min on one core; writes graph_fingerprint_100k.json
+
+The fingerprint holds sha256 of the exported arrays (levels, row offsets, neighbour ids, enterpoint, max_layer), the
+same for every prefix checkpoint of `checkpoints` nodes (so a mismatch is localised), and a few literal adjacency lists.
+"""
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+N, DIM, M, EFC = 100_000, 128, 16, 200
+CHECKPOINTS = (10_000, 30_000, 60_000, 100_000)
+
+
+def graph_digest(g):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(g["levels"], np.int32).tobytes())
+    h.update(np.ascontiguousarray(g["row_offs"], np.uint64).tobytes())
+    h.update(np.ascontiguousarray(g["nbrs"], np.uint32).tobytes())
+    h.update(np.array([g["entry"], g["max_layer"]], np.int64).tobytes())
+    return h.hexdigest()
+
+
+def dataset():
+    from redis_hnsw_b200 import data
+
+    x, _ = data.lowrank(N, DIM, r=16, seed=123)
+    levels = data.draw_levels(N, M, seed=42)
+    return x, levels
+
+
+def main():
+    import oracle
+
+    x, levels = dataset()
+    orc = oracle.Oracle(DIM, M, EFC)
+    out = {"n": N, "dim": DIM, "m": M, "ef_construction": EFC, "dataset": "lowrank r=16 sigma=0.05 seed=123",
+           "levels": "draw_levels seed=42", "generator": "oracle/hnsw_oracle.cpp via tests/golden/make_graph_fingerprint.py",
+           "checkpoints": {}}
+    done = 0
+    t0 = time.time()
+    ties = 0
+    oracle.cut_ties(reset=True)
+    for cp in CHECKPOINTS:
+        st = orc.add_batch(x[done:cp], levels[done:cp])
+        ties += int(st[3])
+        done = cp
+        g = orc.export_graph()
+        deg0 = np.diff(g["row_offs"])
+        out["checkpoints"][str(cp)] = {"sha256": graph_digest(g), "edges": int(g["nbrs"].size), "rows": int(deg0.size),
+                                       "max_degree": int(deg0.max()), "entry": g["entry"], "max_layer": g["max_layer"],
+                                       # equal sims of different nodes across a cut so far: (select_neighbors, w evictions)
+                                       "select_ties": oracle.cut_ties()[0], "evict_ties": oracle.cut_ties()[1]}
+        print(cp, out["checkpoints"][str(cp)], "%.0f s" % (time.time() - t0), flush=True)
+    out["heap_ties_met_by_the_oracle"] = ties
+    out["sample_lists"] = {str(i): [int(v) for v in orc.node_neighbors(i, 0)] for i in (0, 1, 777, 50_000, 99_999)}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "graph_fingerprint_100k.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,131 @@
+"""HNSW_BUILD_SPEC: the NODE.ADD stream (core.rs:383-412, 489-599) executed speculatively in windows and committed in
+stream order (csrc/spec.cuh).  The claim is the strongest one a builder can make: the graph is the reference's sequential
+graph, list for list and in list order — at BASELINE configs[0] in full (10 000 nodes) and at 100 000 x 128-d with the
+headline parameters."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from gpu_fixtures import assert_search_parity, case  # noqa: E402
+from test_gpu_build import _assert_same_graph  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("name,n", [
+    ("cfg1_10k_d32_m5", 10000),   # BASELINE configs[0], every node
+    ("d128_m16", 6000),           # configs[1] parameters
+    ("d768_m32", 1200),           # configs[2] shape (bulk-async row copies)
+    ("d96_m8_generic", 1500),     # no staged kernel for this dimension: SPEC hands the stream to the one-warp EXACT kernel
+])
+def test_spec_build_equals_oracle_graph(name, n):
+    import redis_hnsw_b200 as r
+
+    c = case(name)
+    x, levels = c["x"][:n], c["levels"][:n]
+    go = c["graph"] if n == c["n"] else None
+    if go is None:
+        orc = oracle.Oracle(c["dim"], c["m"], c["efc"])
+        orc.add_batch(x, levels)
+        go = orc.export_graph()
+    else:
+        orc = c["oracle"]
+    dev = r.DeviceIndex(c["dim"], c["m"], c["efc"])
+    assert dev.add_batch(x, levels, mode=r.BUILD_SPEC) == 0
+    _assert_same_graph(dev.export_graph(), go)
+    p, op = dev.params(), orc.params()
+    for key in ("node_count", "max_layer", "enterpoint"):
+        assert p[key] == op[key], key
+    st = dev.build_stats()
+    assert st["inserts"] == n - 1
+    if "generic" not in name:
+        assert st["spec_rounds"] > 0 and st["spec_executions"] >= n - 1
+        assert st["spec_rounds"] < n - 1, "no round ever committed more than one insert: speculation is not working"
+    assert_search_parity(dev, orc, c["q"][:200], 10, 64)
+
+
+def test_spec_graph_does_not_depend_on_the_window():
+    """Any speculation error would make the result depend on how many inserts run ahead of the commit point: windows of
+    1 (purely sequential), 8 and 256, the adaptive default and the one-warp EXACT kernel must give ONE graph."""
+    import redis_hnsw_b200 as r
+    from redis_hnsw_b200 import data
+
+    n, dim, m, efc = 12000, 128, 16, 200
+    x, _ = data.lowrank(n, dim, r=16, seed=77)
+    levels = data.draw_levels(n, m, seed=78)
+    graphs = {}
+    for window in (1, 8, 256, 0):
+        dev = r.DeviceIndex(dim, m, efc)
+        dev.set_option("spec_window", window)
+        dev.add_batch(x, levels, mode=r.BUILD_SPEC)
+        graphs[window] = dev.export_graph()
+        st = dev.build_stats()
+        if window == 1:
+            assert st["spec_rounds"] == n - 1 and st["conflicts"] == 0
+    for window in (8, 256, 0):
+        _assert_same_graph(graphs[window], graphs[1])
+    n_exact = 3000
+    dev = r.DeviceIndex(dim, m, efc)
+    dev.add_batch(x[:n_exact], levels[:n_exact], mode=r.BUILD_EXACT)
+    d2 = r.DeviceIndex(dim, m, efc)
+    d2.add_batch(x[:n_exact], levels[:n_exact], mode=r.BUILD_SPEC)
+    _assert_same_graph(d2.export_graph(), dev.export_graph())
+
+
+def test_spec_in_pieces_then_single_adds_and_deletes():
+    """SPEC streams appended to an existing graph, mixed with NODE.ADD / NODE.DEL one at a time: still the oracle's graph
+    (row stamps of earlier calls must not confuse later ones)."""
+    import redis_hnsw_b200 as r
+
+    c = case("d128_m16")
+    x, levels = c["x"], c["levels"]
+    orc = oracle.Oracle(c["dim"], c["m"], c["efc"])
+    dev = r.DeviceIndex(c["dim"], c["m"], c["efc"])
+    cuts = (0, 1, 2, 900, 2500)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        orc.add_batch(x[a:b], levels[a:b])
+        assert dev.add_batch(x[a:b], levels[a:b], mode=r.BUILD_SPEC) == a
+    for i in range(2500, 2540):
+        assert dev.add(x[i], int(levels[i])) == orc.add(x[i], int(levels[i]))
+    for v in (17, 1200, 2510):
+        dev.delete(v)
+        orc.delete(v)
+    orc.add_batch(x[2540:4000], levels[2540:4000])
+    dev.add_batch(x[2540:4000], levels[2540:4000], mode=r.BUILD_SPEC)
+    _assert_same_graph(dev.export_graph(), orc.export_graph())
+
+
+@pytest.mark.timeout(900)
+def test_spec_build_100k_matches_the_oracle_fingerprint():
+    """100 000 x 128-d, M=16, ef_construction=200: the oracle needs ~6 minutes for this graph, so its fingerprint is
+    committed (tests/golden/graph_fingerprint_100k.json, made by tests/golden/make_graph_fingerprint.py from the oracle
+    alone) and the device graph is hashed at the same checkpoints."""
+    import sys
+
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_graph_fingerprint as fp
+    import redis_hnsw_b200 as r
+
+    gold = json.load(open(os.path.join(HERE, "golden", "graph_fingerprint_100k.json")))
+    x, levels = fp.dataset()
+    dev = r.DeviceIndex(fp.DIM, fp.M, fp.EFC)
+    dev.reserve(fp.N)
+    done = 0
+    for cp in fp.CHECKPOINTS:
+        dev.add_batch(x[done:cp], levels[done:cp], mode=r.BUILD_SPEC)
+        done = cp
+        g = dev.export_graph()
+        want = gold["checkpoints"][str(cp)]
+        assert g["nbrs"].size == want["edges"], "edge count differs at %d nodes" % cp
+        assert (g["entry"], g["max_layer"]) == (want["entry"], want["max_layer"])
+        assert fp.graph_digest(g) == want["sha256"], "graph differs from the oracle's at %d nodes" % cp
+    for i, lst in gold["sample_lists"].items():
+        assert [int(v) for v in dev.node_neighbors(int(i), 0)] == lst
+    st = dev.build_stats()
+    assert st["inserts"] == fp.N - 1
+    print("SPEC 100k: %s" % st)
