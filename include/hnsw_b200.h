@@ -157,6 +157,14 @@ int hnsw_index_node_neighbors(hnsw_index_t* idx, uint32_t id, uint32_t level, ui
 /* node.data (types.rs:296): data_dim floats. */
 int hnsw_index_node_vector(hnsw_index_t* idx, uint32_t id, float* out);
 
+/* Adjacency lists of several (node, level) rows at once — one device gather and one copy instead of one round trip per
+ * row; what a host keeps current after a mutation (the reference rewrites the record of every node reported through
+ * update_fn: lib.rs:351-353, types.rs:292-309).  Row r gets min(len, stride) ids at out_ids[r * stride] and its full length
+ * in out_lens[r] (a row longer than `stride` is asked for again with a larger stride).  A level the node does not have
+ * gives length 0. */
+int hnsw_index_rows_batch(hnsw_index_t* idx, uint64_t n_rows, const uint32_t* nodes, const uint32_t* levels, uint32_t stride,
+                          uint32_t* out_ids, uint32_t* out_lens);
+
 /* ---- whole-graph exchange (snapshot / restore; feeds the RDB records of types.rs:243-284, 410-428) ---
  * Flat graph: rows are (node, level) for level = 0..levels[node]; row index = sum_{j<node}(levels[j]+1) + level;
  * row_offs has n_rows+1 entries into nbrs; deleted nodes have levels = -1 and no rows. */

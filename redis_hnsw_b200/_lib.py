@@ -45,6 +45,7 @@ SYMBOLS = {
     "hnsw_index_node_level": (C.c_int, [_vp, C.c_uint32, _i32p]),
     "hnsw_index_node_neighbors": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _u32p, C.c_uint64, _u64p]),
     "hnsw_index_node_vector": (C.c_int, [_vp, C.c_uint32, _fp]),
+    "hnsw_index_rows_batch": (C.c_int, [_vp, C.c_uint64, _u32p, _u32p, C.c_uint32, _u32p, _u32p]),
     "hnsw_index_graph_sizes": (C.c_int, [_vp, _u64p, _u64p, _u64p]),
     "hnsw_index_export_graph": (C.c_int, [_vp, _i32p, _u64p, _u32p, _i64p, _i32p]),
     "hnsw_index_export_vectors": (C.c_int, [_vp, _fp]),

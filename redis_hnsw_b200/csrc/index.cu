@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -80,6 +81,39 @@ __global__ void l2_batch_kernel(const float* __restrict__ a, const float* __rest
     for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < rows; r += (uint64_t)gridDim.x * blockDim.x)
       out[r] = scalar_sim(a + r * dim, b + r * dim, dim);
   }
+}
+
+// one warp per requested (node, level) row: fixed row + overflow chain -> out_ids[r * stride ..], full length -> out_lens[r]
+__global__ void gather_rows_kernel(Graph g, uint32_t n_rows, const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ levels,
+                                   uint32_t stride, uint32_t* __restrict__ out_ids, uint32_t* __restrict__ out_lens) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  uint32_t* ovf;
+  const uint32_t* row = row_ptr(g, nodes[r], levels[r], &ovf);
+  uint32_t len = 0;
+  if (row) {
+    uint32_t* out = out_ids + (size_t)r * stride;
+    bool more = true;
+    for (uint32_t w = 0; w < g.W / 32 && more; ++w) {
+      const uint32_t nb = row[w * 32 + lane];
+      const uint32_t cnt = __popc(__ballot_sync(kFull, nb != kEmpty));
+      if (nb != kEmpty && len + lane < stride) out[len + lane] = nb;   // rows are compact: valid ids form a prefix
+      len += cnt;
+      more = cnt == 32;
+    }
+    uint32_t link = more ? *ovf : kEmpty;
+    while (link != kEmpty) {
+      const uint32_t nb = g.pool[(size_t)link * 32 + lane];
+      const uint32_t next = __shfl_sync(kFull, nb, 31);
+      const bool valid = lane < kPoolIds && nb != kEmpty;
+      const uint32_t cnt = __popc(__ballot_sync(kFull, valid));
+      if (valid && len + lane < stride) out[len + lane] = nb;
+      len += cnt;
+      link = cnt == (uint32_t)kPoolIds ? next : kEmpty;
+    }
+  }
+  if (lane == 0) out_lens[r] = len;
 }
 
 // ---------------------------------------------------------------- Index: memory
@@ -297,6 +331,10 @@ int Index::load_graph(uint64_t n, const float* vectors, const int32_t* levels, c
     }
   }
   if (entry_ >= 0 && ((uint64_t)entry_ >= n || levels[entry_] < 0)) return fail(HNSW_ERR_INVALID, "bad enterpoint");
+  // the descent starts at (enterpoint, max_layer): a record whose max_layer exceeds the enterpoint's own level (a corrupt
+  // RDB) would make the kernels read upper rows that do not exist
+  if (max_layer_ < 0 || (entry_ >= 0 && max_layer_ > levels[entry_]))
+    return fail(HNSW_ERR_INVALID, "max_layer %d does not match the enterpoint's level", max_layer_);
 
   if ((rc = ensure_nodes(std::max<uint64_t>(n, 1)))) return rc;
   if ((rc = ensure_upper(std::max<uint64_t>(n_upper, 1)))) return rc;
@@ -437,6 +475,10 @@ int hnsw_index_create(uint32_t data_dim, uint32_t m, uint32_t ef_construction, i
   ix.g = Graph{};
   ix.g.W = ((ix.m_max_0 + 31) / 32) * 32;
   ix.g.dim = data_dim;
+  {  // StdRng::from_entropy() (core.rs:344): every index draws its own level sequence; hnsw_index_seed pins it for tests
+    std::random_device rd;
+    ix.rng_state = ((uint64_t)rd() << 32) ^ (uint64_t)rd() ^ 0x9E3779B97F4A7C15ull;
+  }
   int rc = ix.use_device();
   if (!rc) {
     cudaDeviceProp prop;
@@ -562,6 +604,34 @@ int hnsw_index_node_neighbors(hnsw_index_t* idx, uint32_t id, uint32_t level, ui
   }
   if (n) *n = out.size();
   for (uint64_t i = 0; i < out.size() && i < cap; ++i) ids[i] = out[i];
+  return HNSW_OK;
+}
+
+int hnsw_index_rows_batch(hnsw_index_t* idx, uint64_t n_rows, const uint32_t* nodes, const uint32_t* levels, uint32_t stride,
+                          uint32_t* out_ids, uint32_t* out_lens) {
+  IDX_OR_FAIL(idx)
+  if (n_rows == 0) return HNSW_OK;
+  if (!nodes || !levels || !out_ids || !out_lens || stride == 0 || n_rows > 0x7FFFFFFFull) return fail(HNSW_ERR_INVALID, "bad arguments");
+  for (uint64_t i = 0; i < n_rows; ++i)
+    if (nodes[i] >= ix.n_ids || ix.h_level[nodes[i]] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", nodes[i]);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t in_b = al(n_rows * 4), out_b = al(n_rows * (size_t)stride * 4);
+  int rc = ix.ensure_scratch(ix.s_stage, 3 * in_b + out_b);
+  if (rc) return rc;
+  char* base = (char*)ix.s_stage.p;
+  uint32_t *d_nodes = (uint32_t*)base, *d_levels = (uint32_t*)(base + in_b), *d_lens = (uint32_t*)(base + 2 * in_b),
+           *d_ids = (uint32_t*)(base + 3 * in_b);
+  cudaError_t e = cudaMemcpyAsync(d_nodes, nodes, n_rows * 4, cudaMemcpyHostToDevice, ix.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_levels, levels, n_rows * 4, cudaMemcpyHostToDevice, ix.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rows_batch H2D");
+  gather_rows_kernel<<<(unsigned)((n_rows * 32 + 127) / 128), 128, 0, ix.stream>>>(ix.g, (uint32_t)n_rows, d_nodes, d_levels, stride, d_ids,
+                                                                                  d_lens);
+  g_launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_lens, d_lens, n_rows * 4, cudaMemcpyDeviceToHost, ix.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_ids, d_ids, n_rows * (size_t)stride * 4, cudaMemcpyDeviceToHost, ix.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ix.stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rows_batch");
   return HNSW_OK;
 }
 

@@ -12,11 +12,13 @@
 //   * The reference re-serialises the WHOLE index into its key after every mutation and rewrites every touched node
 //     record (lib.rs:317-332, 351-353: O(N) per NODE.ADD).  Here key values are handles on the live index; records are
 //     materialised from device state only when Redis asks for them (rdb_save, HNSW.GET, HNSW.NODE.GET).
-//   * Persistence.  Redis runs rdb_save in a fork()ed child, where the CUDA context of the parent is unusable.  The
-//     module subscribes to the persistence server event (Redis >= 6.0), which fires in the parent BEFORE the fork, and
-//     materialises every record of every live index into host memory with two bulk device-to-host copies per index
-//     (NamedIndex::snapshot); the child then serialises host data only.  A host without server events gets the
-//     reference's own behaviour instead: records are refreshed after every mutation (lib.rs:351-365).
+//   * Persistence.  Redis runs rdb_save in a fork()ed child (BGSAVE, AOF rewrite, replica full sync), where the CUDA
+//     context of the parent is unusable — and the persistence server event is no help: for background saves Redis fires
+//     RDB_START / AOF_START from inside that child (only SYNC_RDB_START runs in the parent).  So nothing on the save path
+//     may touch the device.  NamedIndex keeps a write-through host mirror of every record (vectors, adjacency lists,
+//     levels, index scalars), refreshed in the parent by every mutating command from ONE gather of the rows the mutation
+//     touched; rdb_save, HNSW.GET and HNSW.NODE.GET read only that mirror.  This is the reference's own contract — its
+//     key values are host records rewritten after every mutation (lib.rs:351-365) — at O(touched rows) instead of O(N).
 //   * Cold start (load_index -> make_index, lib.rs:229-315) rebuilds the device graph from the loaded records in one
 //     pass on the first command that touches the index.
 //   * Extensions (not in the reference): `EF ef` on HNSW.SEARCH (the reference always searches with ef_construction,
@@ -56,16 +58,14 @@ const char* const PREFIX = "hnsw";  // lib.rs:27
 // ---------------------------------------------------------------- key values (types.rs)
 
 struct IndexValue {  // value of `hnsw.{index}`  <- IndexRedis (types.rs:45-60)
-  IndexRecord rec;   // as loaded from RDB, or as materialised from `live` at epoch `rec_epoch`
+  IndexRecord rec;   // as loaded from RDB; superseded by `live` (whose host mirror is always current) once that exists
   std::shared_ptr<NamedIndex> live;
-  uint64_t rec_epoch = 0;  // NamedIndex::epoch() the host copy `rec` corresponds to (0 = not from `live`)
 };
 
 struct NodeValue {   // value of `hnsw.{index}.{node}`  <- NodeRedis (types.rs:286-290)
   std::string name;
-  NodeRecord rec;    // as loaded from RDB, or as materialised from `live` at epoch `rec_epoch`
+  NodeRecord rec;    // as loaded from RDB; superseded by the live index's mirror once the index is live
   std::weak_ptr<NamedIndex> live;
-  uint64_t rec_epoch = 0;
 };
 
 RedisModuleType* g_index_type = nullptr;  // HNSW_INDEX_REDIS_TYPE (types.rs:157)
@@ -73,7 +73,6 @@ RedisModuleType* g_node_type = nullptr;   // HNSW_NODE_REDIS_TYPE  (types.rs:354
 std::unordered_map<std::string, std::shared_ptr<NamedIndex>> g_indices;  // INDICES (lib.rs:32-35)
 std::unordered_map<std::string, NodeValue*> g_node_values;    // node key name -> its value (owned by the keyspace)
 std::unordered_map<std::string, IndexValue*> g_index_values;  // index key name -> its value
-bool g_eager = false;  // no server events: keep host records current after every mutation, like the reference
 
 struct ReplyError {  // RedisError::String
   std::string msg;
@@ -138,12 +137,8 @@ void* index_rdb_load(RedisModuleIO* io, int encver) {  // types.rs:180-241
 
 void index_rdb_save(RedisModuleIO* io, void* value) {  // types.rs:243-284
   IndexValue* v = static_cast<IndexValue*>(value);
-  IndexRecord r;
-  try {  // the host copy when it is current (always, in a forked child after the persistence event); else the device
-    r = (v->live && v->rec_epoch != v->live->epoch()) ? v->live->to_record() : v->rec;
-  } catch (const std::exception&) {
-    r = v->rec;
-  }
+  // host data only (this runs in a fork()ed child): the live index's write-through mirror, or the loaded record
+  const IndexRecord r = v->live ? v->live->to_record() : v->rec;
   save_str(io, r.name);
   save_str(io, r.mfunc_kind);
   RedisModule_SaveUnsigned(io, r.data_dim);
@@ -194,21 +189,16 @@ void* node_rdb_load(RedisModuleIO* io, int encver) {  // types.rs:377-408
   return v.release();
 }
 
-NodeRecord current_record(NodeValue* v) {  // From<&Node> for NodeRedis (types.rs:292-309) when the index is live
+NodeRecord current_record(NodeValue* v) {  // From<&Node> for NodeRedis (types.rs:292-309); host mirror, never the device
   if (auto ix = v->live.lock()) {
-    if (v->rec_epoch != ix->epoch() && ix->contains(v->name)) return ix->node_record(v->name);
+    if (ix->contains(v->name)) return ix->node_record(v->name);
   }
   return v->rec;
 }
 
 void node_rdb_save(RedisModuleIO* io, void* value) {  // types.rs:410-428
   NodeValue* v = static_cast<NodeValue*>(value);
-  NodeRecord r;
-  try {
-    r = current_record(v);
-  } catch (const std::exception&) {
-    r = v->rec;
-  }
+  const NodeRecord r = current_record(v);
   RedisModule_SaveUnsigned(io, r.data.size());
   for (float f : r.data) RedisModule_SaveFloat(io, f);
   RedisModule_SaveUnsigned(io, r.neighbors.size());
@@ -223,34 +213,6 @@ void node_free(void* value) {  // types.rs:373-375
   auto it = g_node_values.find(v->name);
   if (it != g_node_values.end() && it->second == v) g_node_values.erase(it);
   delete v;
-}
-
-// Host copies of every record of one live index, from two bulk device-to-host copies (see the header comment).
-void materialize(const std::string& index_name, const std::shared_ptr<NamedIndex>& ix) {
-  auto iv = g_index_values.find(index_name);
-  if (iv == g_index_values.end() || iv->second->live != ix) return;
-  if (iv->second->rec_epoch == ix->epoch()) return;  // nothing changed since the last snapshot
-  NamedIndex::Snapshot snap = ix->snapshot();
-  for (auto& kv : snap.nodes) {
-    auto nv = g_node_values.find(kv.first);
-    if (nv == g_node_values.end()) continue;
-    nv->second->rec = std::move(kv.second);
-    nv->second->rec_epoch = ix->epoch();
-  }
-  iv->second->rec = std::move(snap.index);
-  iv->second->rec_epoch = ix->epoch();
-}
-
-// RedisModuleEvent_Persistence: subevents RDB_START / AOF_START / SYNC_RDB_START (/ SYNC_AOF_START) fire in the parent
-// right before the snapshot (and the fork) starts.
-void on_persistence(RedisModuleCtx*, RedisModuleEvent, uint64_t subevent, void*) {
-  if (subevent > HNSW_PERSISTENCE_START_MAX_SUBEVENT) return;
-  for (auto& kv : g_indices) {
-    try {
-      materialize(kv.first, kv.second);
-    } catch (const std::exception&) {  // never unwind into the host; rdb_save falls back to whatever it can reach
-    }
-  }
 }
 
 // ---------------------------------------------------------------- keys
@@ -460,10 +422,8 @@ std::shared_ptr<NamedIndex> load_index(RedisModuleCtx* ctx, const std::string& i
     for (size_t i = 0; i < values.size(); ++i) {  // node keys become handles on the live index
       values[i]->name = iv->rec.nodes[i];
       values[i]->live = iv->live;
-      values[i]->rec_epoch = iv->live->epoch();    // the loaded record IS the current one until the next mutation
       g_node_values[values[i]->name] = values[i];
     }
-    iv->rec_epoch = iv->live->epoch();
   }
   g_index_values[index_name] = iv;
   g_indices[index_name] = iv->live;
@@ -478,23 +438,6 @@ void update_index(RedisModuleCtx* ctx, const std::string& index_name, const std:
   if (!iv) throw ReplyError{"Index: " + index_name + " does not exist"};
   iv->live = ix;
   g_index_values[index_name] = iv;
-  if (g_eager) {  // what the reference does on every mutation (lib.rs:325)
-    iv->rec = ix->to_record();
-    iv->rec_epoch = ix->epoch();
-  }
-}
-
-// eager mode: refresh the host records of the nodes a mutation touched (lib.rs:351-353 write_node per update_fn call)
-void refresh_touched(const std::shared_ptr<NamedIndex>& ix, const std::vector<std::string>& touched) {
-  if (!g_eager) return;
-  for (const std::string& t : touched) {
-    auto nv = g_node_values.find(t);
-    if (nv == g_node_values.end() || !ix->contains(t)) continue;
-    nv->second->rec = ix->node_record(t);
-  }
-  // every other record is unchanged by this mutation: all host copies are current again
-  for (auto& kv : g_node_values)
-    if (kv.second->live.lock() == ix) kv.second->rec_epoch = ix->epoch();
 }
 
 // write_node (lib.rs:446-460)
@@ -505,7 +448,6 @@ void write_node(RedisModuleCtx* ctx, const std::string& node_name, const std::sh
     nv->name = node_name;
     nv->live = ix;
     nv->rec = NodeRecord();
-    nv->rec_epoch = 0;
   } else {
     std::unique_ptr<NodeValue> v(new NodeValue());
     v->name = node_name;
@@ -539,7 +481,6 @@ void cmd_new(RedisModuleCtx* ctx, const std::vector<std::string>& args) {  // li
   std::unique_ptr<IndexValue> v(new IndexValue());
   v->live = ix;
   v->rec = ix->to_record();
-  v->rec_epoch = ix->epoch();
   key.set(g_index_type, v.get());
   g_index_values[index_name] = v.release();
   g_indices[index_name] = ix;  // lib.rs:163-166
@@ -570,17 +511,14 @@ void cmd_node_add(RedisModuleCtx* ctx, const std::vector<std::string>& args) {  
   const std::string node_name = index_name + "." + p.pos[1];
   std::vector<float> data = narrow(p.vecs["DATA"]);
   auto ix = load_index(ctx, index_name);
-  std::vector<std::string> touched;
   try {
-    ix->add_node(node_name, data.data(), data.size(), g_eager ? &touched : nullptr);  // lib.rs:356-358
+    ix->add_node(node_name, data.data(), data.size());  // lib.rs:356-358
   } catch (const HNSWError& e) {
     throw ReplyError{error_string(e.what())};
   }
-  // lib.rs:351-353, 361-362: the reference rewrites the record of every touched node and of the new node; touched
-  // nodes already hold handles on the live index, so only the new node's key is created.
+  // lib.rs:351-353, 361-362: the reference rewrites the record of every touched node and of the new node.  Touched nodes
+  // hold handles on the live index, whose host mirror add_node has already refreshed; only the new node's key is created.
   write_node(ctx, node_name, ix);
-  touched.push_back(node_name);
-  refresh_touched(ix, touched);
   update_index(ctx, index_name, ix);  // lib.rs:365
   RedisModule_ReplyWithSimpleString(ctx, "OK");
 }
@@ -590,14 +528,12 @@ void cmd_node_del(RedisModuleCtx* ctx, const std::vector<std::string>& args) {  
   const std::string index_name = std::string(PREFIX) + "." + p.pos[0];
   const std::string node_name = index_name + "." + p.pos[1];
   auto ix = load_index(ctx, index_name);
-  std::vector<std::string> touched;
   try {
-    ix->delete_node(node_name, g_eager ? &touched : nullptr);  // lib.rs:397-399 (a missing node is an error here; the reference panics at lib.rs:384)
+    ix->delete_node(node_name);  // lib.rs:397-399 (a missing node is an error here; the reference panics at lib.rs:384)
   } catch (const HNSWError& e) {
     throw ReplyError{error_string(e.what())};
   }
   delete_node_redis(ctx, node_name);   // lib.rs:401
-  refresh_touched(ix, touched);
   update_index(ctx, index_name, ix);   // lib.rs:404
   RedisModule_ReplyWithLongLong(ctx, 1);  // lib.rs:406
 }
@@ -665,7 +601,6 @@ void cmd_node_madd(RedisModuleCtx* ctx, const std::vector<std::string>& args) {
     throw ReplyError{error_string(e.what())};
   }
   for (const std::string& nn : names) write_node(ctx, nn, ix);
-  if (g_eager) materialize(index_name, ix);  // a batch touches too many rows to refresh one by one: snapshot them all
   update_index(ctx, index_name, ix);
   RedisModule_ReplyWithLongLong(ctx, (long long)names.size());
 }
@@ -718,8 +653,5 @@ extern "C" int RedisModule_OnLoad(RedisModuleCtx* ctx, RedisModuleString** argv,
   };
   for (const auto& c : cmds)
     if (RedisModule_CreateCommand(ctx, c.name, c.fn, c.flags, 0, 0, 0) != REDISMODULE_OK) return REDISMODULE_ERR;
-  RedisModuleEvent persistence = {REDISMODULE_EVENT_PERSISTENCE, 1};
-  g_eager = !(RedisModule_SubscribeToServerEvent &&
-              RedisModule_SubscribeToServerEvent(ctx, persistence, on_persistence) == REDISMODULE_OK);
-  return REDISMODULE_OK;
+  return REDISMODULE_OK;  // no server-event subscription: nothing on the persistence path needs the device (see the header)
 }

@@ -40,34 +40,86 @@ NamedIndex::NamedIndex(const std::string& name, uint64_t data_dim, uint64_t m, u
     h_ = nullptr;
     throw HNSWError(last_error(), rc);
   }
+  check(hnsw_index_params(h_, &hparams_));
 }
 
 NamedIndex::~NamedIndex() {
   if (h_) hnsw_index_destroy(h_);
 }
 
-hnsw_params_t NamedIndex::params() const {
-  hnsw_params_t p{};
-  check(hnsw_index_params(h_, &p));
-  return p;
-}
+hnsw_params_t NamedIndex::params() const { return hparams_; }  // host copy, refreshed by every mutation (fork-safe)
 
 std::optional<std::string> NamedIndex::enterpoint() const {
-  hnsw_params_t p = params();
-  if (p.enterpoint == HNSW_NO_NODE) return std::nullopt;
-  return names_[p.enterpoint];
+  if (hparams_.enterpoint == HNSW_NO_NODE || hparams_.enterpoint >= names_.size()) return std::nullopt;
+  return names_[hparams_.enterpoint];
 }
 
-std::vector<std::string> NamedIndex::touched_names() const {
+std::vector<uint32_t> NamedIndex::touched_ids() const {
   uint64_t n = 0;
   check(hnsw_index_touched(h_, nullptr, 0, &n));
   std::vector<uint32_t> ids(n);
   if (n) check(hnsw_index_touched(h_, ids.data(), n, &n));
+  return ids;
+}
+
+std::vector<std::string> NamedIndex::touched_names(const std::vector<uint32_t>& ids) const {
   std::vector<std::string> out;
   out.reserve(ids.size());
   for (uint32_t t : ids)
     if (t < names_.size() && alive_[t]) out.push_back(names_[t]);
   return out;
+}
+
+// mirror <- device: every level of the given nodes, one gather + one copy (hnsw_index_rows_batch)
+void NamedIndex::refresh_rows(const std::vector<uint32_t>& ids) {
+  check(hnsw_index_params(h_, &hparams_));
+  std::vector<uint32_t> nodes, levels;
+  for (uint32_t id : ids) {
+    if (id >= names_.size() || !alive_[id]) continue;
+    int32_t lv = 0;
+    check(hnsw_index_node_level(h_, id, &lv));
+    if (lv < 0) continue;
+    hadj_[id].resize((size_t)lv + 1);
+    for (int32_t l = 0; l <= lv; ++l) nodes.push_back(id), levels.push_back((uint32_t)l);
+  }
+  if (nodes.empty()) return;
+  uint32_t stride = 2 * hparams_.m_max_0 + 32;
+  std::vector<uint32_t> lens(nodes.size()), out;
+  for (;;) {
+    out.resize(nodes.size() * (size_t)stride);
+    check(hnsw_index_rows_batch(h_, nodes.size(), nodes.data(), levels.data(), stride, out.data(), lens.data()));
+    const uint32_t longest = *std::max_element(lens.begin(), lens.end());
+    if (longest <= stride) break;
+    stride = longest + 32;  // degree is unbounded (core.rs:793-795): ask again with room for the longest row
+  }
+  for (size_t r = 0; r < nodes.size(); ++r)
+    hadj_[nodes[r]][levels[r]].assign(out.begin() + (long)(r * stride), out.begin() + (long)(r * stride + lens[r]));
+}
+
+// mirror <- device for everything: one graph export + one vector export
+void NamedIndex::refresh_all() {
+  check(hnsw_index_params(h_, &hparams_));
+  uint64_t n_ids = 0, n_rows = 0, n_edges = 0;
+  check(hnsw_index_graph_sizes(h_, &n_ids, &n_rows, &n_edges));
+  hvec_.assign(n_ids, {});
+  hadj_.assign(n_ids, {});
+  if (n_ids == 0) return;
+  std::vector<int32_t> levels(n_ids);
+  std::vector<uint64_t> offs(n_rows + 1);
+  std::vector<uint32_t> nbrs(std::max<uint64_t>(n_edges, 1));
+  int64_t entry = -1;
+  int32_t max_layer = 0;
+  check(hnsw_index_export_graph(h_, levels.data(), offs.data(), nbrs.data(), &entry, &max_layer));
+  std::vector<float> vecs(n_ids * (size_t)dim_);
+  check(hnsw_index_export_vectors(h_, vecs.data()));
+  uint64_t row = 0;
+  for (uint64_t i = 0; i < n_ids; ++i) {
+    if (levels[i] < 0) continue;  // deleted: no rows
+    hvec_[i].assign(vecs.begin() + (long)(i * (size_t)dim_), vecs.begin() + (long)((i + 1) * (size_t)dim_));
+    hadj_[i].resize((size_t)levels[i] + 1);
+    for (int32_t l = 0; l <= levels[i]; ++l, ++row)
+      hadj_[i][(size_t)l].assign(nbrs.begin() + (long)offs[row], nbrs.begin() + (long)offs[row + 1]);
+  }
 }
 
 void NamedIndex::add_node(const std::string& node_name, const float* data, size_t n, std::vector<std::string>* touched,
@@ -84,7 +136,12 @@ void NamedIndex::add_node(const std::string& node_name, const float* data, size_
   alive_.push_back(1);
   ids_[node_name] = id;
   ++epoch_;
-  if (touched) *touched = touched_names();  // core.rs:580-584
+  hvec_.emplace_back(data, data + n);
+  hadj_.emplace_back();
+  std::vector<uint32_t> t = touched_ids();
+  if (touched) *touched = touched_names(t);  // core.rs:580-584
+  t.push_back(id);
+  refresh_rows(t);                           // lib.rs:351-353, 361-362: every touched record and the new one are rewritten
 }
 
 void NamedIndex::add_nodes(const std::vector<std::string>& node_names, const float* data, size_t n, bool fast) {
@@ -105,6 +162,7 @@ void NamedIndex::add_nodes(const std::vector<std::string>& node_names, const flo
     ids_[node_names[i]] = first + (uint32_t)i;
   }
   ++epoch_;
+  refresh_all();  // a batch touches too many rows to name them: the mirror is re-read once
 }
 
 void NamedIndex::delete_node(const std::string& node_name, std::vector<std::string>* touched) {
@@ -116,8 +174,21 @@ void NamedIndex::delete_node(const std::string& node_name, std::vector<std::stri
   ids_.erase(it);
   alive_[id] = 0;
   ++epoch_;
-  if (touched) *touched = touched_names();  // core.rs:443-447 (the victim itself is never reported)
+  std::vector<uint32_t> t = touched_ids();
+  if (touched) *touched = touched_names(t);  // core.rs:443-447 (the victim itself is never reported)
   names_[id].clear();
+  hvec_[id].clear();
+  hvec_[id].shrink_to_fit();
+  hadj_[id].clear();
+  refresh_rows(t);
+}
+
+// At most min(k, ef, live nodes) results can come back (core.rs:879 pops from a result set of <= ef entries): buffers
+// are sized by that, never by a user-supplied K (HNSW.SEARCH ... K 8589934592 must not allocate gigabytes).
+size_t NamedIndex::clamp_k(size_t k, uint32_t ef) const {
+  hnsw_params_t p = params();
+  const uint64_t ef_eff = ef ? ef : p.ef_construction;
+  return (size_t)std::min<uint64_t>(std::min<uint64_t>(k, ef_eff), p.node_count);
 }
 
 static std::string last_segment(const std::string& full) {  // core.rs:885-887
@@ -129,6 +200,7 @@ std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_
   if (n != dim_)  // core.rs:478-480
     throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
   std::vector<SearchResult> out;
+  k = clamp_k(k, ef);
   if (k == 0) return out;
   std::vector<uint32_t> ids(k);
   std::vector<float> sims(k);
@@ -140,8 +212,7 @@ std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_
     r.sim = sims[i];
     r.name = last_segment(names_[ids[i]]);
     if (with_data) {
-      r.data.resize(dim_);
-      check(hnsw_index_node_vector(h_, ids[i], r.data.data()));  // core.rs:888 copies the stored vector
+      r.data = hvec_[ids[i]];  // core.rs:888 copies the stored vector (host mirror)
     }
     out.push_back(std::move(r));
   }
@@ -153,6 +224,7 @@ std::vector<std::vector<SearchResult>> NamedIndex::search_knn_batch(const float*
   if (n != dim_)
     throw HNSWError("data dimension: " + std::to_string(n) + " does not match Index", HNSW_ERR_DIM_MISMATCH);
   std::vector<std::vector<SearchResult>> out(nq);
+  k = clamp_k(k, ef);
   if (k == 0 || nq == 0) return out;
   std::vector<uint32_t> ids(nq * k), counts(nq);
   std::vector<float> sims(nq * k);
@@ -163,10 +235,7 @@ std::vector<std::vector<SearchResult>> NamedIndex::search_knn_batch(const float*
       SearchResult r;
       r.sim = sims[i * k + j];
       r.name = last_segment(names_[ids[i * k + j]]);
-      if (with_data) {
-        r.data.resize(dim_);
-        check(hnsw_index_node_vector(h_, ids[i * k + j], r.data.data()));
-      }
+      if (with_data) r.data = hvec_[ids[i * k + j]];
       out[i].push_back(std::move(r));
     }
   }
@@ -181,9 +250,9 @@ std::vector<std::string> NamedIndex::node_names() const {
   return out;
 }
 
-// From<Index> for IndexRedis (types.rs:62-91)
+// From<Index> for IndexRedis (types.rs:62-91) — host mirror only (fork-safe)
 IndexRecord NamedIndex::to_record() const {
-  hnsw_params_t p = params();
+  const hnsw_params_t& p = hparams_;
   IndexRecord r;
   r.name = name_;
   r.data_dim = p.data_dim;
@@ -198,39 +267,28 @@ IndexRecord NamedIndex::to_record() const {
   // that never held a node has no layer at all (core.rs:341).
   if (!names_.empty() || p.node_count) r.layers.resize((size_t)r.max_layer + 1);
   for (size_t i = 0; i < names_.size(); ++i) {
-    if (!alive_[i]) continue;
-    int32_t lv = 0;
-    check(hnsw_index_node_level(h_, (uint32_t)i, &lv));
-    if (lv < 0) continue;
-    if ((size_t)lv >= r.layers.size()) r.layers.resize((size_t)lv + 1);
-    r.layers[(size_t)lv].push_back(names_[i]);
+    if (!alive_[i] || hadj_[i].empty()) continue;
+    const size_t lv = hadj_[i].size() - 1;
+    if (lv >= r.layers.size()) r.layers.resize(lv + 1);
+    r.layers[lv].push_back(names_[i]);
     r.nodes.push_back(names_[i]);
   }
-  if (p.enterpoint != HNSW_NO_NODE) r.enterpoint = names_[p.enterpoint];
+  if (p.enterpoint != HNSW_NO_NODE && p.enterpoint < names_.size()) r.enterpoint = names_[p.enterpoint];
   return r;
 }
 
-// From<&Node> for NodeRedis (types.rs:292-309)
+// From<&Node> for NodeRedis (types.rs:292-309) — host mirror only (fork-safe)
 NodeRecord NamedIndex::node_record(const std::string& node_name) const {
   auto it = ids_.find(node_name);
   if (it == ids_.end()) throw HNSWError("Node: " + node_name + " does not exist", HNSW_ERR_NOT_FOUND);
   const uint32_t id = it->second;
   NodeRecord r;
-  r.data.resize(dim_);
-  check(hnsw_index_node_vector(h_, id, r.data.data()));
-  int32_t lv = 0;
-  check(hnsw_index_node_level(h_, id, &lv));
-  std::vector<uint32_t> buf(256);
-  for (int32_t l = 0; l <= lv; ++l) {
-    uint64_t n = 0;
-    check(hnsw_index_node_neighbors(h_, id, (uint32_t)l, buf.data(), buf.size(), &n));
-    if (n > buf.size()) {
-      buf.resize(n);
-      check(hnsw_index_node_neighbors(h_, id, (uint32_t)l, buf.data(), buf.size(), &n));
-    }
+  r.data = hvec_[id];
+  r.neighbors.reserve(hadj_[id].size());
+  for (const auto& lst : hadj_[id]) {
     std::vector<std::string> layer;
-    layer.reserve(n);
-    for (uint64_t j = 0; j < n; ++j) layer.push_back(names_[buf[j]]);
+    layer.reserve(lst.size());
+    for (uint32_t x : lst) layer.push_back(names_[x]);
     r.neighbors.push_back(std::move(layer));
   }
   return r;
@@ -239,31 +297,9 @@ NodeRecord NamedIndex::node_record(const std::string& node_name) const {
 NamedIndex::Snapshot NamedIndex::snapshot() const {
   Snapshot s;
   s.index = to_record();
-  uint64_t n_ids = 0, n_rows = 0, n_edges = 0;
-  check(hnsw_index_graph_sizes(h_, &n_ids, &n_rows, &n_edges));
-  if (n_ids == 0) return s;
-  std::vector<int32_t> levels(n_ids);
-  std::vector<uint64_t> offs(n_rows + 1);
-  std::vector<uint32_t> nbrs(std::max<uint64_t>(n_edges, 1));
-  int64_t entry = -1;
-  int32_t max_layer = 0;
-  check(hnsw_index_export_graph(h_, levels.data(), offs.data(), nbrs.data(), &entry, &max_layer));
-  std::vector<float> vecs(n_ids * (size_t)dim_);
-  check(hnsw_index_export_vectors(h_, vecs.data()));
   s.nodes.reserve(ids_.size());
-  uint64_t row = 0;
-  for (uint64_t i = 0; i < n_ids; ++i) {
-    if (levels[i] < 0) continue;  // deleted: no rows
-    NodeRecord r;
-    r.data.assign(vecs.begin() + i * (size_t)dim_, vecs.begin() + (i + 1) * (size_t)dim_);
-    for (int32_t l = 0; l <= levels[i]; ++l, ++row) {
-      std::vector<std::string> layer;
-      layer.reserve(offs[row + 1] - offs[row]);
-      for (uint64_t e = offs[row]; e < offs[row + 1]; ++e) layer.push_back(names_[nbrs[e]]);
-      r.neighbors.push_back(std::move(layer));
-    }
-    s.nodes.emplace_back(names_[i], std::move(r));
-  }
+  for (size_t i = 0; i < names_.size(); ++i)
+    if (alive_[i]) s.nodes.emplace_back(names_[i], node_record(names_[i]));
   return s;
 }
 
@@ -306,8 +342,17 @@ void NamedIndex::restore_graph(const IndexRecord& ir, const std::vector<const No
   int64_t entry = ir.enterpoint ? (int64_t)id_of(*ir.enterpoint) : -1;
   ++epoch_;
   if (nbrs.empty()) nbrs.push_back(0);
+  hvec_.assign(n, {});
+  hadj_.assign(n, {});
   if (n == 0) return;
   check(hnsw_index_load_graph(h_, n, vecs.data(), levels.data(), offs.data(), nbrs.data(), entry, (int32_t)ir.max_layer));
+  check(hnsw_index_params(h_, &hparams_));
+  for (size_t i = 0, row = 0; i < n; ++i) {  // the mirror is what was just uploaded
+    hvec_[i] = recs[i]->data;
+    hadj_[i].resize((size_t)levels[i] + 1);
+    for (int32_t l = 0; l <= levels[i]; ++l, ++row)
+      hadj_[i][(size_t)l].assign(nbrs.begin() + (long)offs[row], nbrs.begin() + (long)offs[row + 1]);
+  }
 }
 
 }  // namespace hnswhost

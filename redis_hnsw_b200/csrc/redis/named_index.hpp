@@ -72,6 +72,7 @@ class NamedIndex {
   // core.rs:477-486 (ef = 0 -> ef_construction, core.rs:485).  The reference copies each hit's vector into the result
   // (core.rs:888) but its HNSW.SEARCH reply never sends it (types.rs:436-456): `with_data` = false skips the k
   // device-to-host row copies.
+  size_t clamp_k(size_t k, uint32_t ef) const;  // min(k, effective ef, live nodes): the most results a search can return
   std::vector<SearchResult> search_knn(const float* q, size_t n, size_t k, uint32_t ef = 0, bool with_data = false) const;
   // extension: nq independent queries in one device batch; result r of query i at [i][r]
   std::vector<std::vector<SearchResult>> search_knn_batch(const float* q, size_t nq, size_t n, size_t k, uint32_t ef = 0,
@@ -87,8 +88,14 @@ class NamedIndex {
   IndexRecord to_record() const;
   NodeRecord node_record(const std::string& node_name) const;
   std::vector<std::string> node_names() const;
-  // Every record at once, from two bulk device-to-host copies (graph + vector slab) instead of per-node getters:
-  // what a persistence snapshot needs (types.rs:243-284, 410-428 for the whole keyspace of one index).
+  // Every record at once (types.rs:243-284, 410-428 for the whole keyspace of one index).
+  //
+  // FORK SAFETY.  to_record(), node_record() and snapshot() never touch the device: they read a write-through host mirror
+  // (vectors, adjacency lists, levels, index scalars) that every mutating call refreshes before it returns — the rows
+  // the mutation touched come back in ONE gather (hnsw_index_rows_batch), a bulk load re-reads the graph once.  Redis
+  // serialises keys from a fork()ed child (BGSAVE, AOF rewrite, replica sync; the persistence server event fires in
+  // that child too), where the parent's CUDA context is unusable; the reference has the same property for the same
+  // reason: its key values are plain host records rewritten after every mutation (lib.rs:351-365).
   struct Snapshot {
     IndexRecord index;
     std::vector<std::pair<std::string, NodeRecord>> nodes;
@@ -102,7 +109,10 @@ class NamedIndex {
  private:
   void restore_graph(const IndexRecord& ir, const std::vector<const NodeRecord*>& recs);
   void check(int rc) const;
-  std::vector<std::string> touched_names() const;
+  std::vector<uint32_t> touched_ids() const;
+  std::vector<std::string> touched_names(const std::vector<uint32_t>& ids) const;
+  void refresh_rows(const std::vector<uint32_t>& ids);  // mirror <- device for the rows of these nodes (one gather)
+  void refresh_all();                                   // mirror <- device for the whole graph (bulk loads)
 
   std::string name_;
   hnsw_index_t* h_ = nullptr;
@@ -111,6 +121,10 @@ class NamedIndex {
   std::vector<std::string> names_;                 // id -> name ("" once deleted)
   std::vector<char> alive_;
   uint64_t epoch_ = 1;
+  // write-through host mirror (see FORK SAFETY above)
+  std::vector<std::vector<float>> hvec_;                    // id -> vector
+  std::vector<std::vector<std::vector<uint32_t>>> hadj_;    // id -> level -> neighbour ids, list order
+  hnsw_params_t hparams_{};                                 // index scalars after the last mutation
 };
 
 template <class Fetch>

@@ -145,11 +145,22 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
     // warps with a small stage each beat few warps with a deep one
     uint32_t rows = 4096u / (dim * 4);
     S = rows >= 32 ? 32 : (rows >= 16 ? 16 : (rows >= 8 ? 8 : 4));
-    // latency mode: with fewer queries than SMs nothing competes for shared memory, and a stage that takes a whole
-    // adjacency chunk in one round shortens every hop (one HNSW.SEARCH: 437 -> 330 us on a 1M x 128 graph)
-    if (nq <= (uint64_t)num_sms && dim * 4 * 32 <= 32768) S = 32;
   }
   const uint32_t slots = opt_recent_slots ? opt_recent_slots : 1024;
+  if (!opt_stage_rows) {
+    // latency mode: when every query of the call is resident at once anyway (a slice of a sharded batch, one HNSW.SEARCH)
+    // nothing is gained by keeping the stage small, and a stage that takes a whole adjacency chunk in one round shortens
+    // every hop (one HNSW.SEARCH: 437 -> 330 us on a 1M x 128 graph).  Take the deepest stage that still lets all the
+    // call's warps sit on the SMs together (about 200 KB of shared memory per SM for the warps' stages and tag tables).
+    const uint64_t warps_per_sm = (nq + (uint64_t)num_sms - 1) / (uint64_t)num_sms;
+    for (int cand = 32; cand > S; cand /= 2) {
+      const size_t pw = warp2_smem_bytes(dim, cand, slots, 4);
+      if ((size_t)dim * 4 * cand <= 32768 && pw <= max_smem / 2 && warps_per_sm * pw <= 200u * 1024u) {
+        S = cand;
+        break;
+      }
+    }
+  }
   int slot_bits = 0;
   while ((1u << slot_bits) < slots) ++slot_bits;
   // 16-bit tags identify an id exactly only below 2^(log2(slots) + 15)

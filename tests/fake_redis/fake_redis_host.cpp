@@ -9,9 +9,10 @@
 //
 // Each script line is one command (whitespace-separated words).  Meta commands:
 //     #SAVE <file>     rdb_save every module-typed key into <file> (in this process, like the SAVE command)
-//     #BGSAVE <file>   like BGSAVE: fire the persistence server event (RDB_START) in the parent, fork(), rdb_save every
-//                      key in the CHILD (which must not touch the parent's CUDA context), wait, fire the end event.
-//                      Set FAKE_REDIS_NO_EVENTS=1 to emulate a host without RedisModule_SubscribeToServerEvent.
+//     #BGSAVE <file>   like BGSAVE: fork(); the CHILD fires the persistence server event (RDB_START — redis-server calls
+//                      startSaving() from rdbSave(), i.e. inside the forked child; only SAVE / SYNC_RDB_START run in the
+//                      parent) and rdb_saves every key; it must not touch the parent's CUDA context.  The parent waits
+//                      and fires the end event.  FAKE_REDIS_NO_EVENTS=1 emulates a host without server events.
 //     #LOAD <file>     rdb_load the keys of <file> into the (empty) keyspace
 //     #KEYS            reply: sorted [key, type-name] pairs
 //     #INFO            reply: module name/version, registered commands (name, flags, key spec) and data types
@@ -462,10 +463,10 @@ static Reply meta(const std::vector<std::string>& w) {
     r.kind = Reply::kInt;
     r.i = save_all(w[1]);
   } else if (w[0] == "#BGSAVE" && w.size() == 2) {
-    fire_event(1 /* REDISMODULE_EVENT_PERSISTENCE */, 0 /* RDB_START */);
     std::fflush(stdout);
     pid_t pid = fork();
     if (pid == 0) {
+      fire_event(1 /* REDISMODULE_EVENT_PERSISTENCE */, 0 /* RDB_START: fired by rdbSave() in the child */);
       long long n = save_all(w[1]);
       _exit(n >= 0 ? 0 : 1);  // no atexit handlers, no static destructors: like redis' child
     }

@@ -22,6 +22,12 @@ sys.path.insert(0, ROOT)
 
 N, DIM, M, EFC = 100_000, 128, 16, 200
 CHECKPOINTS = (10_000, 30_000, 60_000, 100_000)
+# The data seed was chosen (first of 123, 124, ... 127 tried) so that the oracle meets NO tie across a select_neighbors cut
+# during the build: where two different nodes tie for the m-th place the reference's choice is an accident of BinaryHeap
+# layout, and a fixture must not pin accidents.  Seeds 123 / 124 / 125 meet 1 / 2 / 4 such ties,
+# 126 and 127 none (the `select_ties` field of every checkpoint).
+DATA_SEED = int(os.environ.get("FP_DATA_SEED", "126"))
+LEVEL_SEED = 42
 
 
 def graph_digest(g):
@@ -36,8 +42,8 @@ def graph_digest(g):
 def dataset():
     from redis_hnsw_b200 import data
 
-    x, _ = data.lowrank(N, DIM, r=16, seed=123)
-    levels = data.draw_levels(N, M, seed=42)
+    x, _ = data.lowrank(N, DIM, r=16, seed=DATA_SEED)
+    levels = data.draw_levels(N, M, seed=LEVEL_SEED)
     return x, levels
 
 
@@ -46,8 +52,8 @@ def main():
 
     x, levels = dataset()
     orc = oracle.Oracle(DIM, M, EFC)
-    out = {"n": N, "dim": DIM, "m": M, "ef_construction": EFC, "dataset": "lowrank r=16 sigma=0.05 seed=123",
-           "levels": "draw_levels seed=42", "generator": "oracle/hnsw_oracle.cpp via tests/golden/make_graph_fingerprint.py",
+    out = {"n": N, "dim": DIM, "m": M, "ef_construction": EFC, "dataset": "lowrank r=16 sigma=0.05 seed=%d" % DATA_SEED,
+           "levels": "draw_levels seed=%d" % LEVEL_SEED, "generator": "oracle/hnsw_oracle.cpp via tests/golden/make_graph_fingerprint.py",
            "checkpoints": {}}
     done = 0
     t0 = time.time()
@@ -66,7 +72,8 @@ def main():
         print(cp, out["checkpoints"][str(cp)], "%.0f s" % (time.time() - t0), flush=True)
     out["heap_ties_met_by_the_oracle"] = ties
     out["sample_lists"] = {str(i): [int(v) for v in orc.node_neighbors(i, 0)] for i in (0, 1, 777, 50_000, 99_999)}
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "graph_fingerprint_100k.json"), "w") as fh:
+    name = os.environ.get("FP_OUT", "graph_fingerprint_100k.json")
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), name), "w") as fh:
         json.dump(out, fh, indent=1)
 
 
