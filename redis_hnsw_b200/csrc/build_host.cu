@@ -485,7 +485,13 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   uint32_t h[kSpecCtlWords];
   uint32_t prev_exec = 0, prev_dist = 0, prev_repr = 0, prev_waste = 0;
   const bool trace = std::getenv("HNSW_BUILD_TRACE") != nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  double k1_ms = 0, k2_ms = 0, host_ms = 0;
+  if (trace)
+    for (auto& x : ev) cudaEventCreate(&x);
+  auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   while (f < end) {
+    const double t_round = trace ? now_ms() : 0;
     uint32_t B = opt_spec_window ? opt_spec_window : (uint32_t)std::max(8.0, 4.0 * ema);
     B = std::min(std::min(B, resident), end - f);
     // a node that raises max_layer becomes the enterpoint of everything after it (core.rs:587-593): the window ends there
@@ -503,15 +509,24 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     a.verU = d_verU;
     LaunchCfg c1{(int)B, 32, smem, stream};
     g_launches++;
+    if (trace) cudaEventRecord(ev[0], stream);
     e = run_spec(kind, efr, small, c1, g, a, false, nullptr);
     if (e != cudaSuccess) return cuda_fail(e, "spec_exec launch");
+    if (trace) cudaEventRecord(ev[1], stream);
     g_launches++;
     spec_commit_kernel<<<1, 256, 0, stream>>>(g, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "spec_commit launch");
+    if (trace) cudaEventRecord(ev[2], stream);
     e = cudaMemcpyAsync(h, a.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return cuda_fail(e, "spec round");
+    if (trace) {
+      float a_ms = 0, b_ms = 0;
+      cudaEventElapsedTime(&a_ms, ev[0], ev[1]);
+      cudaEventElapsedTime(&b_ms, ev[1], ev[2]);
+      k1_ms += a_ms, k2_ms += b_ms, host_ms += now_ms() - t_round;
+    }
     const uint32_t committed = h[kSpecCommitted], reason = h[kSpecReason];
     pool_used = h[kSpecPoolUsed];
     max_layer = (int32_t)h[kSpecMaxLayer];
@@ -527,8 +542,11 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     build_stats_ex[9 - 4] += h[kSpecDistWasted] - prev_waste;
     build_stats_ex[11 - 4] = std::max<uint64_t>(build_stats_ex[11 - 4], B);
     prev_exec = h[kSpecExecuted], prev_dist = h[kSpecDistEvals], prev_repr = h[kSpecReprunesDone], prev_waste = h[kSpecDistWasted];
-    if (trace && (build_stats_ex[7 - 4] % 256) == 1)
-      std::fprintf(stderr, "[spec] f=%u window=%u committed=%u reason=%u ema=%.1f\n", f, B, committed, reason, ema);
+    if (trace && (build_stats_ex[7 - 4] % 1024) == 0) {
+      std::fprintf(stderr, "[spec] f=%u window=%u committed=%u reason=%u ema=%.1f | last 1024 rounds: K1 %.3f ms, K2 %.3f ms, round (host clock) %.3f ms\n",
+                   f, B, committed, reason, ema, k1_ms / 1024, k2_ms / 1024, host_ms / 1024);
+      k1_ms = k2_ms = host_ms = 0;
+    }
     f += committed;
     node_count += committed;
     ema = 0.8 * ema + 0.2 * committed;
@@ -554,6 +572,8 @@ int Index::add_spec(uint32_t first, uint32_t count) {
       return fail(HNSW_ERR_CUDA, "speculative builder made no progress at node %u (reason %u)", f, reason);
     }
   }
+  if (trace)
+    for (auto& x : ev) cudaEventDestroy(x);
   return HNSW_OK;
 }
 
@@ -692,16 +712,38 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
     start = 1;
   }
   const uint32_t rest = (uint32_t)count - start;
+  const uint64_t live_before = node_count;
   // ef_construction < m: select_neighbors at core.rs:531 is a genuine 2-hop sweep (build.cuh header), which only the
   // EXACT kernels compute; the batched builder would link ef_construction instead of m neighbours per node
   if (mode == HNSW_BUILD_EXACT || ef_construction < m) {
-    if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)rest * (m_max_0 + 8) * 2 + 4096))) return rc;
-    rc = add_exact(first + start, rest, want_touched);
-    if (!rc) node_count += rest;
-    return rc;
+    // overflow rows: the stream can allocate one per append in the worst case, but rows over W ids are rare (1-3 % of the
+    // nodes): reserve for a bounded burst and let long streams run in pieces
+    for (uint32_t pos = 0; pos < rest && !rc; pos += 65536) {
+      const uint32_t piece = std::min<uint32_t>(65536, rest - pos);
+      if ((rc = pull_meta())) break;  // the device owns pool_used
+      if ((rc = ensure_pool((uint64_t)pool_used + (uint64_t)piece * (m_max_0 + 8) * 2 + 4096))) break;
+      const uint64_t seen = build_stats[0];
+      rc = add_exact(first + start + pos, piece, want_touched);
+      node_count += rc ? (build_stats[0] - seen) : piece;   // on failure: the inserts the kernel completed
+    }
+  } else if (mode == HNSW_BUILD_SPEC) {
+    rc = add_spec(first + start, rest);
+  } else {
+    rc = add_fast(first + start, rest);
   }
-  if (mode == HNSW_BUILD_SPEC) return add_spec(first + start, rest);
-  return add_fast(first + start, rest);
+  if (rc) {
+    // The ids were handed out before the kernels ran.  Nodes that were not (completely) inserted must not stay live: they
+    // become tombstones (level -1) on host and device, so that no later call treats them as members of the graph and the
+    // host layers can resynchronise their name tables from n_ids (orphan ids after a failed add).
+    const uint64_t first_bad = std::min<uint64_t>(n_ids, (uint64_t)first + start + (node_count - live_before));
+    for (uint64_t i = first_bad; i < n_ids; ++i) h_level[i] = -1;
+    if (first_bad < n_ids) cudaMemsetAsync(g.level + first_bad, 0xFF, (n_ids - first_bad) * 4, stream);
+    cudaStreamSynchronize(stream);
+    const std::string keep = g_last_error;
+    pull_meta();
+    g_last_error = keep;
+  }
+  return rc;
 }
 
 }  // namespace hnsw

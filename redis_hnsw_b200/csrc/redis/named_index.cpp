@@ -130,7 +130,12 @@ void NamedIndex::add_node(const std::string& node_name, const float* data, size_
   if (!ids_.empty() && ids_.count(node_name))
     throw HNSWError("Node: " + rust_debug_str(node_name) + " already exists", HNSW_ERR_EXISTS);
   uint32_t id = 0;
-  check(hnsw_index_add(h_, data, n, level, &id));
+  const int rc = hnsw_index_add(h_, data, n, level, &id);
+  if (rc != HNSW_OK) {
+    const std::string why = last_error();
+    resync_ids();  // a failed add still consumed its id (now a tombstone): keep the name table aligned with the device
+    throw HNSWError(why, rc);
+  }
   if (id != names_.size()) throw HNSWError("device id out of sequence");
   names_.push_back(node_name);
   alive_.push_back(1);
@@ -154,15 +159,36 @@ void NamedIndex::add_nodes(const std::vector<std::string>& node_names, const flo
       if (ids_.count(nn) || seen[nn]++) throw HNSWError("Node: " + rust_debug_str(nn) + " already exists", HNSW_ERR_EXISTS);
   }
   uint32_t first = 0;
-  check(hnsw_index_add_batch(h_, node_names.size(), data, nullptr, fast ? HNSW_BUILD_FAST : HNSW_BUILD_EXACT, &first));
-  if (first != names_.size()) throw HNSWError("device id out of sequence");
+  const int rc = hnsw_index_add_batch(h_, node_names.size(), data, nullptr, fast ? HNSW_BUILD_FAST : HNSW_BUILD_SPEC, &first);
+  if (rc != HNSW_OK && first != names_.size()) {
+    const std::string why = last_error();
+    resync_ids();
+    throw HNSWError(why, rc);
+  }
+  // on a failure part-way the nodes that made it are live and named; the rest of the ids are tombstones
   for (size_t i = 0; i < node_names.size(); ++i) {
-    names_.push_back(node_names[i]);
-    alive_.push_back(1);
-    ids_[node_names[i]] = first + (uint32_t)i;
+    int32_t lv = -1;
+    const bool live = hnsw_index_node_level(h_, first + (uint32_t)i, &lv) == HNSW_OK && lv >= 0;
+    names_.push_back(live ? node_names[i] : std::string());
+    alive_.push_back(live ? 1 : 0);
+    if (live) ids_[node_names[i]] = first + (uint32_t)i;
   }
   ++epoch_;
   refresh_all();  // a batch touches too many rows to name them: the mirror is re-read once
+  if (rc != HNSW_OK) throw HNSWError(last_error(), rc);
+}
+
+// after a failed mutation: every id the device handed out has an entry here (dead ones unnamed)
+void NamedIndex::resync_ids() {
+  hnsw_params_t p{};
+  if (hnsw_index_params(h_, &p) != HNSW_OK) return;
+  while (names_.size() < p.n_ids) {
+    names_.emplace_back();
+    alive_.push_back(0);
+    hvec_.emplace_back();
+    hadj_.emplace_back();
+  }
+  hparams_ = p;
 }
 
 void NamedIndex::delete_node(const std::string& node_name, std::vector<std::string>* touched) {
@@ -208,6 +234,7 @@ std::vector<SearchResult> NamedIndex::search_knn(const float* q, size_t n, size_
   check(hnsw_index_search(h_, q, n, (uint32_t)k, ef, ids.data(), sims.data(), &cnt));
   out.reserve(cnt);
   for (uint32_t i = 0; i < cnt; ++i) {
+    if (ids[i] >= names_.size() || !alive_[ids[i]]) continue;  // never hand out an id without a name
     SearchResult r;
     r.sim = sims[i];
     r.name = last_segment(names_[ids[i]]);
@@ -232,6 +259,7 @@ std::vector<std::vector<SearchResult>> NamedIndex::search_knn_batch(const float*
   for (size_t i = 0; i < nq; ++i) {
     out[i].reserve(counts[i]);
     for (uint32_t j = 0; j < counts[i]; ++j) {
+      if (ids[i * k + j] >= names_.size() || !alive_[ids[i * k + j]]) continue;
       SearchResult r;
       r.sim = sims[i * k + j];
       r.name = last_segment(names_[ids[i * k + j]]);

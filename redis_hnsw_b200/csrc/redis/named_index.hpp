@@ -65,7 +65,8 @@ class NamedIndex {
                 int level = -1);
   // extension: a NODE.ADD stream of `count` nodes in one call (hnsw_index_add_batch).  fast = true uses the batched
   // builder (HNSW_BUILD_FAST: same per-insert algorithm, nodes of one batch do not see each other); false is the
-  // sequentially consistent stream.  All names are checked before anything is inserted.
+  // sequentially consistent stream (HNSW_BUILD_SPEC: speculative windows committed in order, the graph of one-by-one
+  // NODE.ADDs).  All names are checked before anything is inserted.
   void add_nodes(const std::vector<std::string>& node_names, const float* data, size_t n, bool fast);
   // core.rs:414-475
   void delete_node(const std::string& node_name, std::vector<std::string>* touched = nullptr);
@@ -113,6 +114,7 @@ class NamedIndex {
   std::vector<std::string> touched_names(const std::vector<uint32_t>& ids) const;
   void refresh_rows(const std::vector<uint32_t>& ids);  // mirror <- device for the rows of these nodes (one gather)
   void refresh_all();                                   // mirror <- device for the whole graph (bulk loads)
+  void resync_ids();                                    // name table <- n_ids after a failed add (dead ids stay unnamed)
 
   std::string name_;
   hnsw_index_t* h_ = nullptr;

@@ -287,7 +287,13 @@ class Index:
             raise HNSWError("data dimension: %d does not match Index" % data.size, _lib.ERR_DIM_MISMATCH)  # :390
         if self._dev.params()["node_count"] > 0 and name in self._ids:
             raise HNSWError("Node: %r already exists" % name, _lib.ERR_EXISTS)  # :407-409
-        nid = self._dev.add(data, level)
+        try:
+            nid = self._dev.add(data, level)
+        except HNSWError:
+            # a failed add still consumed its id (a tombstone on the device): keep the name table aligned
+            while len(self._names) < self._dev.params()["n_ids"]:
+                self._names.append(None)
+            raise
         assert nid == len(self._names)
         self._ids[name] = nid
         self._names.append(name)
@@ -314,4 +320,4 @@ class Index:
             raise HNSWError("data dimension: %d does not match Index" % data.size, _lib.ERR_DIM_MISMATCH)  # :479
         ids, sims = self._dev.search(data, k, ef)
         return [SearchResult(float(s), self._names[int(i)].split(".")[-1], self._dev.node_vector(int(i)))
-                for i, s in zip(ids, sims)]
+                for i, s in zip(ids, sims) if int(i) < len(self._names) and self._names[int(i)] is not None]

@@ -23,9 +23,12 @@ class _DevPtr:
 
 def replicate_index(dev, rank, world, src=0):
     """Broadcast the device buffers of `dev` on rank `src` into the (same-parameter) index of every other rank.
-    One ncclBroadcast per buffer: vector slab, adjacency rows, overflow links, levels, pool, meta."""
+    One ncclBroadcast per buffer: vector slab, adjacency rows, overflow links, levels, pool, meta.
+    Returns (bytes broadcast, seconds of the broadcasts on this rank) — (0, 0.0) for a single rank."""
     if world == 1:
-        return
+        return 0, 0.0
+    import time
+
     import torch
     import torch.distributed as dist
 
@@ -34,12 +37,44 @@ def replicate_index(dev, rank, world, src=0):
     dist.broadcast(lay, src)
     if rank != src:
         dev.prepare_replica(lay.cpu().numpy().astype(np.uint64))
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    total = 0
     for ptr, nbytes in dev.device_buffers():
         if nbytes:
             dist.broadcast(torch.as_tensor(_DevPtr(ptr, nbytes), device="cuda"), src)
+            total += nbytes
     torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
     if rank != src:
         dev.adopt_replica()
+    return total, secs
+
+
+def result_checksum(ids, sims):
+    """Order-sensitive 64-bit checksum of a result block (ids [n, k] u32, sims [n, k] f32 compared as bits): equal on two
+    ranks iff they returned the same neighbours with the same sims in the same places (up to hash collisions)."""
+    a = np.ascontiguousarray(ids, dtype=np.uint32).astype(np.uint64).ravel()
+    b = np.ascontiguousarray(sims, dtype=np.float32).view(np.uint32).astype(np.uint64).ravel()
+    pos = np.arange(1, a.size + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h = (a * np.uint64(0x9E3779B97F4A7C15) + b * np.uint64(0xC2B2AE3D27D4EB4F) + pos) * (pos | np.uint64(1))
+        return int(np.bitwise_xor.reduce(h ^ (h >> np.uint64(29))))
+
+
+def ranks_agree(checksum, world, device=None):
+    """True iff every rank computed the same checksum (all-gather of one int64 per rank)."""
+    if world == 1:
+        return True, [checksum]
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([checksum & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    vals = [int(p.item()) for p in parts]
+    return all(v == vals[0] for v in vals), vals
 
 
 def gather_results(ids, sims, counts, nq_total, rank, world, device=None):
