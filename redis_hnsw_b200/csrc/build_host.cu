@@ -546,6 +546,19 @@ int Index::add_spec(uint32_t first, uint32_t count) {
       std::fprintf(stderr, "[spec] f=%u window=%u committed=%u reason=%u ema=%.1f | last 1024 rounds: K1 %.3f ms, K2 %.3f ms, round (host clock) %.3f ms\n",
                    f, B, committed, reason, ema, k1_ms / 1024, k2_ms / 1024, host_ms / 1024);
       k1_ms = k2_ms = host_ms = 0;
+      // where and for how long every warp of this round's K1 ran (slot headers still hold the round's diagnostics)
+      std::vector<uint32_t> hh((size_t)ring * kSpecHdrWords);
+      if (cudaMemcpy(hh.data(), a.hdr, hh.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        uint32_t t_min = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < B; ++i) t_min = std::min(t_min, hh[(size_t)((a.frontier + i) & (ring - 1)) * kSpecHdrWords + kSpecT0]);
+        std::fprintf(stderr, "[spec]   K1 warps (slot: sm, start us, run us, x = executed):");
+        for (uint32_t i = 0; i < B; ++i) {
+          const uint32_t* w = &hh[(size_t)((a.frontier + i) & (ring - 1)) * kSpecHdrWords];
+          std::fprintf(stderr, " %u:%u,%.0f,%.0f%s", i, w[kSpecSm] & 0xFFFFu, (w[kSpecT0] - t_min) / 1e3, w[kSpecDur] / 1e3,
+                       (w[kSpecSm] & 0x80000000u) ? "x" : "");
+        }
+        std::fprintf(stderr, "\n");
+      }
     }
     f += committed;
     node_count += committed;

@@ -41,13 +41,13 @@ def device_index(name):
     return idx
 
 
-def assert_search_parity(dev, orc, q, k, ef, check_stats=True):
+def assert_search_parity(dev, orc, q, k, ef, check_stats=True, min_tie_free=0.9):
     """IDs and result counts bit-exact, sims bit-exact, work counters equal — on every query where the oracle
     met no tie between different nodes (the reference leaves tie order to BinaryHeap internals)."""
     ids, sims, counts, st = dev.search_batch(q, k, ef=ef, stats=True)
     oids, osims, ocounts, ost, _ = orc.search_batch(q, k, ef=ef)
     tie_free = ost[:, 3] == 0
-    assert tie_free.mean() > 0.9
+    assert tie_free.mean() > min_tie_free
     assert np.array_equal(counts[tie_free], ocounts[tie_free])
     assert np.array_equal(ids[tie_free], oids[tie_free])
     assert np.array_equal(sims[tie_free].view(np.uint32), osims[tie_free].view(np.uint32))

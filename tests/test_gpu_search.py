@@ -128,7 +128,9 @@ def test_ef_up_to_1024():
     c = case("d128_m16")
     dev = device_index("d128_m16")
     for ef in (600, 1024):
-        assert_search_parity(dev, c["oracle"], c["q"][:200], 10, ef)
+        # a list of 600 / 1024 entries holds 10-17 % of this 6000-node graph: equal sims between far-away nodes are met by
+        # most queries, so the tie-free subset the ids are compared on is smaller than at the usual ef
+        assert_search_parity(dev, c["oracle"], c["q"][:400], 10, ef, min_tie_free=0.05)
     n = 1500
     orc = oracle.Oracle(c["dim"], c["m"], 700)
     orc.add_batch(c["x"][:n], c["levels"][:n])
@@ -269,6 +271,6 @@ def test_errors_and_empty_index():
     ids, sims, counts = dev.search_batch(np.zeros((4, 32), np.float32), 5)
     assert np.all(counts == 0) and np.all(ids == 0xFFFFFFFF)
     with pytest.raises(r.HNSWError, match="not supported"):
-        dev.search_batch(np.zeros((4, 32), np.float32), 5, ef=1000)
+        dev.search_batch(np.zeros((4, 32), np.float32), 5, ef=5000)
     with pytest.raises(r.HNSWError):
         r.DeviceIndex(0, 5, 100)
