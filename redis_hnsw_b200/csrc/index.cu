@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -478,6 +479,8 @@ int hnsw_index_create(uint32_t data_dim, uint32_t m, uint32_t ef_construction, i
   {  // StdRng::from_entropy() (core.rs:344): every index draws its own level sequence; hnsw_index_seed pins it for tests
     std::random_device rd;
     ix.rng_state = ((uint64_t)rd() << 32) ^ (uint64_t)rd() ^ 0x9E3779B97F4A7C15ull;
+    // test hook for hosts that cannot call hnsw_index_seed (the Redis module in a fresh process): a pinned level sequence
+    if (const char* s = std::getenv("HNSW_LEVEL_SEED")) ix.rng_state = std::strtoull(s, nullptr, 10) ^ 0x9E3779B97F4A7C15ull;
   }
   int rc = ix.use_device();
   if (!rc) {

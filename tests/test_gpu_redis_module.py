@@ -189,7 +189,8 @@ def test_node_madd_bulk_load(tmp_path, fast, events):
     leave a consistent keyspace that survives BGSAVE + reload."""
     n, dim, m, efc = 400, 32, 5, 48
     x, q = data.uniform(n, dim, seed=21, n_queries=8)
-    env = None if events else {"FAKE_REDIS_NO_EVENTS": "1"}
+    # the engine seeds its level RNG from entropy (core.rs:344); both processes of the FAST 0 comparison pin it instead
+    env = dict({"HNSW_LEVEL_SEED": "7"}, **({} if events else {"FAKE_REDIS_NO_EVENTS": "1"}))
     rdb = str(tmp_path / "m.fake_rdb")
     madd = "HNSW.NODE.MADD idx FAST %d NODES %d %s DATA %d %d %s" % (
         fast, n - 1, " ".join("n%d" % i for i in range(1, n)), n - 1, dim, " ".join(_vec(v) for v in x[1:]))

@@ -42,13 +42,16 @@ static inline float sim(uint32_t a, uint32_t b) {
 
 struct Read {
   uint64_t row;
-  int kind;        // 0 strict, 1 search (query = the insert's node), 2 sweep (query = e)
+  int kind;        // 0 strict (a row that is re-selected: its content decides), 1 search (query = the insert's node),
+                   // 2 sweep (query = e), 3 append target (read-modify-write: only "does the append cross the cap" matters),
+                   // 4 remove target (only the presence of the removed id matters)
   uint32_t qnode;  // node whose vector the changed ids are compared with
   float thr;       // -inf: list not full
 };
 struct Write {
   uint64_t row;
   std::vector<uint32_t> diff;
+  int op;  // 0 replace, 1 append, 2 remove
 };
 struct Log {
   std::vector<Read> reads;
@@ -94,21 +97,21 @@ static std::vector<P> search_level(uint32_t q, uint32_t ep, int ef, int lvl) {
   return out;
 }
 
-static void log_write(uint32_t node, int lvl, std::vector<uint32_t> diff) {
-  if (LOG) LOG->writes.push_back({key(node, lvl), std::move(diff)});
+static void log_write(uint32_t node, int lvl, std::vector<uint32_t> diff, int op = 0) {
+  if (LOG) LOG->writes.push_back({key(node, lvl), std::move(diff), op});
 }
-static void log_strict(uint32_t node, int lvl) {
-  if (LOG) LOG->reads.push_back({key(node, lvl), 0, 0, 0});
+static void log_strict(uint32_t node, int lvl, int kind = 0) {
+  if (LOG) LOG->reads.push_back({key(node, lvl), kind, 0, 0});
 }
 
 static void add_nb(uint32_t a, int lvl, uint32_t b) {
   auto& l = NB[a][lvl];
-  if (std::find(l.begin(), l.end(), b) == l.end()) l.push_back(b), log_write(a, lvl, {b});
+  if (std::find(l.begin(), l.end(), b) == l.end()) l.push_back(b), log_write(a, lvl, {b}, 1);
 }
 static void rm_nb(uint32_t a, int lvl, uint32_t b) {
   auto& l = NB[a][lvl];
   auto it = std::find(l.begin(), l.end(), b);
-  if (it != l.end()) l.erase(it), log_write(a, lvl, {b});
+  if (it != l.end()) l.erase(it), log_write(a, lvl, {b}, 2);
 }
 
 static uint64_t n_reprunes = 0;
@@ -116,6 +119,7 @@ static uint64_t KH[8];
 
 static void reprune(uint32_t e, int lvl, int cap) {
   std::vector<uint32_t> old = NB[e][lvl];
+  log_strict(e, lvl, 0);  // the row being re-selected: its whole content decides the outcome
   ++epoch;
   stamp[e] = epoch;
   std::vector<P> cand;
@@ -144,8 +148,8 @@ static void reprune(uint32_t e, int lvl, int cap) {
   std::vector<uint32_t> d = add;
   d.insert(d.end(), rem.begin(), rem.end());
   log_write(e, lvl, d);
-  for (uint32_t x : add) log_strict(x, lvl), add_nb(x, lvl, e);
-  for (uint32_t x : rem) log_strict(x, lvl), rm_nb(x, lvl, e);
+  for (uint32_t x : add) log_strict(x, lvl, 3), add_nb(x, lvl, e);
+  for (uint32_t x : rem) log_strict(x, lvl, 4), rm_nb(x, lvl, e);
   ++n_reprunes;
 }
 
@@ -165,7 +169,7 @@ static void insert(uint32_t q) {
     for (size_t i = 0; i < n_sel; ++i) sel.push_back(w[i].second);
     NB[q][lc] = sel;
     log_write(q, lc, sel);
-    for (uint32_t r : sel) log_strict(r, lc), add_nb(r, lc, q);
+    for (uint32_t r : sel) log_strict(r, lc, 3), add_nb(r, lc, q);
     for (uint32_t e : sel)
       if ((int)NB[e][lc].size() > cap) reprune(e, lc, cap);
   }
@@ -220,25 +224,30 @@ int main(int argc, char** argv) {
     for (auto& L : logs) avg_r += L.reads.size(), avg_w += L.writes.size();
     printf("N=%zu window=%zu reads/insert=%.1f writes/insert=%.1f reprunes/insert=%.2f\n", cp, ids.size(), avg_r / ids.size(),
            avg_w / ids.size(), (double)(n_reprunes - r0) / ids.size());
-    for (int fine = 0; fine <= 1; ++fine)
-      for (size_t B : {16, 32, 64, 128, 256, 512, 1024, 2048}) {
+    for (int mode = 0; mode < 4; ++mode)
+      for (size_t B : {16, 64, 256, 1024}) {
+        const int fine = mode & 1, oplog = mode >> 1;
         // average over the disjoint windows of size B inside the logged stretch
-        double dep_frac = 0, depth_sum = 0, prefix_sum = 0, sweeps_cost = 0;
+        double dep_frac = 0, depth_sum = 0, prefix_sum = 0, sweeps_cost = 0, sprefix_sum = 0, redo_sum = 0;
         size_t nw = ids.size() / B;
         for (size_t wdx = 0; wdx < nw; ++wdx) {
           std::unordered_map<uint64_t, std::vector<std::pair<int, const Write*>>> wr;
           std::vector<int> depth(B, 0);
-          size_t n_dep = 0, prefix = B;
+          size_t n_dep = 0, prefix = B, sprefix = B, redo_in_sprefix = 0;
           int maxd = 0;
           for (size_t i = 0; i < B; ++i) {
             const Log& L = logs[wdx * B + i];
             int d = 0;
+            bool search_dep = false, commit_dep = false;
             for (const Read& r : L.reads) {
               auto it = wr.find(r.row);
               if (it == wr.end()) continue;
               for (auto& jw : it->second) {
                 bool hit = true;
-                if (fine && r.kind != 0) {
+                if (oplog && r.kind == 3 && jw.second->op == 1) hit = false;        // two appends commute (no cap crossing: see header)
+                else if (oplog && r.kind == 4 && jw.second->op != 0) hit = false;   // remove of one id vs append / remove of another
+                else if (oplog && (r.kind == 3 || r.kind == 4)) hit = true;
+                else if (fine && (r.kind == 1 || r.kind == 2)) {
                   hit = false;
                   if (r.thr == -INFINITY) hit = true;
                   else
@@ -246,7 +255,8 @@ int main(int argc, char** argv) {
                       if (z != r.qnode && sim(r.qnode, z) > r.thr) hit = true;
                 }
                 if (hit) d = std::max(d, depth[jw.first] + 1);
-                if (hit && fine && B == 64) KH[r.kind + (r.kind == 1 && r.thr == -INFINITY ? 2 : 0) + ((r.row >> 32) ? 4 : 0)]++;
+                if (hit) (r.kind == 1 ? search_dep : commit_dep) = true;
+
               }
             }
             depth[i] = d;
@@ -254,25 +264,28 @@ int main(int argc, char** argv) {
               ++n_dep;
               if (prefix == B) prefix = i;
             }
+            if (sprefix == B) {
+              if (search_dep) sprefix = i;
+              else if (commit_dep) ++redo_in_sprefix;
+            }
             maxd = std::max(maxd, d);
             for (const Write& w : L.writes) wr[w.row].push_back({(int)i, &w});
           }
           dep_frac += (double)n_dep / B;
           depth_sum += maxd + 1;
           prefix_sum += prefix;
+          sprefix_sum += sprefix;
+          redo_sum += redo_in_sprefix;
           // executions if every insert at chain depth d runs d+1 times (upper bound of the Jacobi re-executions)
           double ex = 0;
           for (size_t i = 0; i < B; ++i) ex += depth[i] + 1;
           sweeps_cost += ex / B;
         }
         if (nw)
-          printf("  %s B=%4zu  dependent=%.3f  sweeps=%.2f  inserts/sweep=%.1f  prefix=%.1f  exec/insert<=%.2f\n", fine ? "fine  " : "coarse", B,
-                 dep_frac / nw, depth_sum / nw, B / (depth_sum / nw), prefix_sum / nw, sweeps_cost / nw);
+          printf("  %s%s B=%4zu  dependent=%.3f  inserts/sweep=%.1f  prefix=%.1f | search-only prefix=%.1f with %.1f link-phase redos inside\n",
+                 fine ? "fine  " : "coarse", oplog ? "+oplog" : "      ", B, dep_frac / nw, B / (depth_sum / nw), prefix_sum / nw, sprefix_sum / nw,
+                 redo_sum / nw);
       }
-    printf("  fine hits at B=64 by kind: L0 strict=%llu search=%llu sweep=%llu search-notfull=%llu | upper strict=%llu search=%llu sweep=%llu notfull=%llu\n",
-           (unsigned long long)KH[0], (unsigned long long)KH[1], (unsigned long long)KH[2], (unsigned long long)KH[3], (unsigned long long)KH[4],
-           (unsigned long long)KH[5], (unsigned long long)KH[6], (unsigned long long)KH[7]);
-    for (auto& k : KH) k = 0;
     fflush(stdout);
   }
   return 0;
