@@ -725,6 +725,9 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
   } else if (n == "recent_ways") {
     if (value != 1 && value != 2) return fail(HNSW_ERR_INVALID, "recent_ways must be 1 or 2");
     ix.opt_recent_ways = (int)value;
+  } else if (n == "lookahead") {
+    if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "lookahead must be 0 or 1");
+    ix.opt_lookahead = (int)value;
   } else if (n == "search_cta") {
     if (value < 0 || value > 1) return fail(HNSW_ERR_INVALID, "search_cta must be 0 or 1");
     ix.opt_search_cta = (int)value;

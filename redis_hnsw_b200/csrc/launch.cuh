@@ -4,6 +4,7 @@
 #include "search.cuh"
 #include "search2.cuh"
 #include "build2.cuh"
+#include "search_la.cuh"
 
 namespace hnsw {
 
@@ -44,6 +45,7 @@ enum KernelId : int {
 constexpr int kKernSearch2Cp = 24;  // search_knn2_kernel with cp.async row copies (RowCopy<C>::kOk): + 2 * log2(S / 4) + (16-bit tags ? 1 : 0)
 constexpr int kKernBuildSearch2 = 32;
 constexpr int kKernSearch2W2 = 52;   // DRAFT search_knn2_kernel, cp.async rows, 2-way visited sets: + log2(S / 4)
+constexpr int kKernSearch2La = 56;   // search_knn2_la_kernel (32-row stage, cp.async rows, one-hop lookahead): + (16-bit tags ? 1 : 0)
 constexpr int kKernSearch2Cta = 48;  // DRAFT search_knn2_cta_kernel (one query per CTA of 4 warps): + (16-bit tags ? 1 : 0)
 constexpr int kKernExact2 = 40;   // insert_exact2_kernel / delete_exact2_kernel (TMA-staged, build2.cuh)
 constexpr int kKernDelete2 = 41;
@@ -124,6 +126,8 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
       case kKernSearch2W2 + 1: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, Way2, 1>), SearchArgs) break;
       case kKernSearch2W2 + 2: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, Way2, 1>), SearchArgs) break;
       case kKernSearch2W2 + 3: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, Way2, 1>), SearchArgs) break;
+      case kKernSearch2La + 0: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_la_kernel<EFR, Dist::C, uint32_t>), SearchArgs) break;
+      case kKernSearch2La + 1: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_la_kernel<EFR, Dist::C, uint16_t>), SearchArgs) break;
       case kKernSearch2Cta + 0: HNSW_RUN((search_knn2_cta_kernel<EFR, Dist::C, uint32_t>), SearchArgs)
       case kKernSearch2Cta + 1: HNSW_RUN((search_knn2_cta_kernel<EFR, Dist::C, uint16_t>), SearchArgs)
       case kKernBuildSearch2 + 0: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint32_t>), FastArgs)

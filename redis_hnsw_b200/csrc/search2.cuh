@@ -84,6 +84,10 @@ __device__ __forceinline__ void cp_async_if(uint32_t dst, const void* src, bool 
   }
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most N of the most recently committed cp.async groups are still in flight
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -152,6 +156,23 @@ struct Recent {
       tab[slot] = tag;
     }
     return true;
+  }
+  // the two halves of test_and_set, for the lookahead (search_la.cuh): true if `nid` is NOT in the table / remember it
+  __device__ __forceinline__ bool test(uint32_t nid) const {
+    if constexpr (sizeof(T) == 4) {
+      return tab[(nid * 2654435761u) >> (32 - bits)] != nid;
+    } else {
+      uint32_t f = (nid * 2654435761u) & ((1u << (bits + 15)) - 1u);
+      return tab[f >> 15] != (T)(0x8000u | (f & 0x7FFFu));
+    }
+  }
+  __device__ __forceinline__ void set(uint32_t nid) {
+    if constexpr (sizeof(T) == 4) {
+      tab[(nid * 2654435761u) >> (32 - bits)] = nid;
+    } else {
+      uint32_t f = (nid * 2654435761u) & ((1u << (bits + 15)) - 1u);
+      tab[f >> 15] = (T)(0x8000u | (f & 0x7FFFu));
+    }
   }
 };
 

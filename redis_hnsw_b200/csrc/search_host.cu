@@ -147,16 +147,21 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
     S = rows >= 32 ? 32 : (rows >= 16 ? 16 : (rows >= 8 ? 8 : 4));
   }
   const uint32_t slots = opt_recent_slots ? opt_recent_slots : 1024;
+  bool use_la = false;
   if (!opt_stage_rows) {
     // latency mode: when every query of the call is resident at once anyway (a slice of a sharded batch, one HNSW.SEARCH)
     // nothing is gained by keeping the stage small, and a stage that takes a whole adjacency chunk in one round shortens
     // every hop (one HNSW.SEARCH: 437 -> 330 us on a 1M x 128 graph).  Take the deepest stage that still lets all the
     // call's warps sit on the SMs together (about 200 KB of shared memory per SM for the warps' stages and tag tables).
     const uint64_t warps_per_sm = (nq + (uint64_t)num_sms - 1) / (uint64_t)num_sms;
-    for (int cand = 32; cand > S; cand /= 2) {
-      const size_t pw = warp2_smem_bytes(dim, cand, slots, 4);
+    const bool cp_kind = opt_row_copy == 1 && (kind == kKindR4 || kind == kKindR1);
+    for (int cand = 32; cand >= S; cand /= 2) {
+      // a 32-row stage of cp.async rows also gets the second stage of the lookahead kernel (search_la.cuh)
+      const bool la = cand == 32 && cp_kind && opt_lookahead;
+      const size_t pw = warp2_smem_bytes(dim, cand, slots, 4) + (la ? la_smem_bytes(dim) : 0);
       if ((size_t)dim * 4 * cand <= 32768 && pw <= max_smem / 2 && warps_per_sm * pw <= 200u * 1024u) {
         S = cand;
+        use_la = la;
         break;
       }
     }
@@ -186,7 +191,7 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
       return HNSW_OK;
     }
   }
-  const size_t per_warp = warp2_smem_bytes(dim, S, slots, tag16 ? 2 : 4);
+  const size_t per_warp = warp2_smem_bytes(dim, S, slots, tag16 ? 2 : 4) + (use_la ? la_smem_bytes(dim) : 0);
   int block = opt_block ? std::min(opt_block, 128) : 64;  // search_knn2_kernel is bounded at 128 threads per CTA
   while (block > 32 && (size_t)(block / 32) * per_warp > max_smem) block /= 2;
   const int warps = block / 32;
@@ -195,8 +200,9 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   // rows of up to two cp.async instructions (32-d, 128-d) are copied with cp.async, longer ones with bulk-async copies
   const bool cp = opt_row_copy == 1 && (kind == kKindR4 || kind == kKindR1);
   int id = search2_id(S, tag16) + (cp ? kKernSearch2Cp - kKernSearch2 : 0);
+  if (use_la) id = kKernSearch2La + (tag16 ? 1 : 0);
   uint32_t table_slots = slots;
-  if (opt_recent_ways == 2 && cp && tag16 && slots >= 128 && n_ids <= (1ull << (slot_bits - 1 + 15))) {
+  if (!use_la && opt_recent_ways == 2 && cp && tag16 && slots >= 128 && n_ids <= (1ull << (slot_bits - 1 + 15))) {
     // DRAFT: the same bytes as `slots` 16-bit tags, organised as slots / 2 two-way sets (one 32-bit word per set)
     table_slots = slots / 2;
     id = kKernSearch2W2 + (S == 4 ? 0 : S == 8 ? 1 : S == 16 ? 2 : 3);

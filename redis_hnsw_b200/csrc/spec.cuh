@@ -21,6 +21,7 @@
 // inserts are dense (every insert rewrites ~46 rows and reads ~350), so a round commits a prefix of O(sqrt N)-ish inserts.
 #pragma once
 #include "build2.cuh"
+#include "search_la.cuh"
 
 namespace hnsw {
 
@@ -244,7 +245,11 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   }
 
   Warp2<C, S, T> w;
-  uint32_t* lists = reinterpret_cast<uint32_t*>(warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane));
+  unsigned char* after = warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane);
+  constexpr bool kLookahead = S == 32 && RowCopy<C>::kOk;          // search_la.cuh: second stage for the next hop's rows
+  LaBuf<C> lb;
+  if constexpr (kLookahead) after = la_setup<C, S, T>(lb, w, after, lane);
+  uint32_t* lists = reinterpret_cast<uint32_t*>(after);
   // sel[m] | old[lcap] | keep_add[lcap + W] | rem[lcap] | edit[lcap] | tmp[lcap] | wkey[wmaxe] | woff[wmaxe]
   uint32_t* sel = lists;
   uint32_t* old = sel + ((a.m + 31) & ~31u);
@@ -273,7 +278,8 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     const bool link = lc <= l;
     const uint32_t cap = lc == 0 ? a.cap0 : a.capU;               // core.rs:560
     load_q_from_slab<C, S, T>(w, g, q, lane);
-    search_layer2<EFR, C, S, T, RowCopy<C>::kDefault>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane, hook);   // :513, :524
+    if constexpr (kLookahead) search_layer2_la<EFR, C, S, T>(g, w, lb, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane, hook);   // :513, :524
+    else search_layer2<EFR, C, S, T, RowCopy<C>::kDefault>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane, hook);
     float s;
     L.get(0, lane, false, ep, s);                                 // :514 / :576
     if (!link) continue;

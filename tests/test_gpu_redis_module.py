@@ -206,5 +206,5 @@ def test_node_madd_bulk_load(tmp_path, fast, events):
     got = R.run(["#LOAD " + rdb] + probe)
     assert got[0] == n + 1 and got[1:] == r[6:]
     if fast == 0:                                                  # same levels, same order -> same graph as one-by-one
-        one = R.run(_build_cmds("idx", x, m, efc) + probe)
+        one = R.run(_build_cmds("idx", x, m, efc) + probe, env=env)
         assert one[n + 1:] == r[6:]
