@@ -155,6 +155,7 @@ __device__ __forceinline__ void reprune_select2(const Graph& g, Warp2<C, S, T>& 
     }
   }
   if (np) flush(np);
+  L.finish(lane);                                                // wide lists (EFR >= 4): back to the sorted layout
 }
 
 // update_node_connections (core.rs:776-822) for node `e` whose re-selected list is in L; shared by insert and delete.
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(32) insert_exact2_kernel(Graph g, ExactArgs a)
   const int lane = lane_id();
   Warp2<C, S, T> w;
   unsigned char* after = warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane);
-  constexpr bool kLookahead = S == 32 && RowCopy<C>::kOk;          // search_la.cuh
+  constexpr bool kLookahead = kLookaheadInBuilders && S == 32 && RowCopy<C>::kOk;          // search_la.cuh
   LaBuf<C> lb;
   if constexpr (kLookahead) after = la_setup<C, S, T>(lb, w, after, lane);
   uint32_t* lists = reinterpret_cast<uint32_t*>(after);

@@ -69,7 +69,7 @@ bool Index::exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) c
   const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
   const uint32_t slots = 8192;
   // 32-d / 128-d rows: a second stage for the one-hop lookahead of the insert's searches (search_la.cuh)
-  const size_t need = warp2_smem_bytes(dim, S, slots, 4) + ((kind == kKindR1 || kind == kKindR4) ? la_smem_bytes(dim) : 0) + list_bytes;
+  const size_t need = warp2_smem_bytes(dim, S, slots, 4) + ((kLookaheadInBuilders && (kind == kKindR1 || kind == kKindR4)) ? la_smem_bytes(dim) : 0) + list_bytes;
   if (need > max_smem) return false;
   *smem = need;
   *vis_slots = slots;
@@ -445,7 +445,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
   const uint32_t vis_slots = 8192, wmaxe = 256, rcap = 2048, wcap = 8192, ring = 1024;
   const size_t list_words = (size_t)((m + 31) & ~31u) + 5 * (size_t)lcap + g.W + 2 * (size_t)wmaxe;
-  const size_t smem = warp2_smem_bytes(dim, S, vis_slots, 4) + ((kind == kKindR1 || kind == kKindR4) ? la_smem_bytes(dim) : 0) +
+  const size_t smem = warp2_smem_bytes(dim, S, vis_slots, 4) + ((kLookaheadInBuilders && (kind == kKindR1 || kind == kKindR4)) ? la_smem_bytes(dim) : 0) +
                       list_words * 4;
   const bool small = m_max_0 <= 64;
   int occ = 0;

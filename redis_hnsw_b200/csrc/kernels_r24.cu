@@ -1,3 +1,3 @@
-// Instantiates the search kernels for one distance mode (DistReg<24>); see search.cuh / launch.cuh.
+// Entry point of one distance mode (DistReg<24>): its list classes are compiled in kernels_r24_p{1,2,3}.cu.
 #include "launch.cuh"
-HNSW_DEFINE_KIND(r24, DistReg<24>)
+HNSW_DECLARE_KIND_PARTS(r24)

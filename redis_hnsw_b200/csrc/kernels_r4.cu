@@ -1,3 +1,3 @@
-// Instantiates the search kernels for one distance mode (DistReg<4>); see search.cuh / launch.cuh.
+// Entry point of one distance mode (DistReg<4>): its list classes are compiled in kernels_r4_p{1,2,3}.cu.
 #include "launch.cuh"
-HNSW_DEFINE_KIND(r4, DistReg<4>)
+HNSW_DECLARE_KIND_PARTS(r4)

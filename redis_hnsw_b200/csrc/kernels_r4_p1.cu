@@ -1,0 +1,3 @@
+// Instantiates the kernels of one distance mode (DistReg<4>) for one group of list classes; see launch.cuh (run_kind).
+#include "launch.cuh"
+HNSW_DEFINE_KIND_PART(r4, DistReg<4>, 1)

@@ -1,3 +1,3 @@
-// Instantiates the SPEC builder's K1 (spec.cuh) for rows of 32 * 4 floats; see spec_launch.cuh.
+// Entry point of the SPEC builder's K1 for rows of 32 * 4 floats: classes compiled in kernels_spec_r4_p{1,2}.cu.
 #include "spec_launch.cuh"
-HNSW_DEFINE_SPEC_KIND(r4, 4)
+HNSW_DECLARE_SPEC_KIND_PARTS(r4)

@@ -126,8 +126,8 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
       case kKernSearch2W2 + 1: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 8, Way2, 1>), SearchArgs) break;
       case kKernSearch2W2 + 2: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 16, Way2, 1>), SearchArgs) break;
       case kKernSearch2W2 + 3: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 32, Way2, 1>), SearchArgs) break;
-      case kKernSearch2La + 0: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_la_kernel<EFR, Dist::C, uint32_t>), SearchArgs) break;
-      case kKernSearch2La + 1: if constexpr (RowCopy<Dist::C>::kOk) HNSW_RUN((search_knn2_la_kernel<EFR, Dist::C, uint16_t>), SearchArgs) break;
+      case kKernSearch2La + 0: if constexpr (RowCopy<Dist::C>::kOk && EFR <= 2) HNSW_RUN((search_knn2_la_kernel<EFR, Dist::C, uint32_t>), SearchArgs) break;
+      case kKernSearch2La + 1: if constexpr (RowCopy<Dist::C>::kOk && EFR <= 2) HNSW_RUN((search_knn2_la_kernel<EFR, Dist::C, uint16_t>), SearchArgs) break;
       case kKernSearch2Cta + 0: HNSW_RUN((search_knn2_cta_kernel<EFR, Dist::C, uint32_t>), SearchArgs)
       case kKernSearch2Cta + 1: HNSW_RUN((search_knn2_cta_kernel<EFR, Dist::C, uint16_t>), SearchArgs)
       case kKernBuildSearch2 + 0: HNSW_RUN((build_search2_kernel<EFR, Dist::C, uint32_t>), FastArgs)
@@ -143,15 +143,25 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
   return cudaErrorInvalidValue;
 }
 
-template <class Dist>
+// PART splits the list classes of one distance kind over translation units (compile time: every class instantiates every
+// kernel): 0 = all classes, 1 = EFR 1 / 2 / 4, 2 = EFR 8 / 16, 3 = EFR 32
+template <class Dist, int PART = 0>
 cudaError_t run_kind(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only, int* occ) {
-  switch (efr) {
-    case 1: return run_kernel<1, Dist>(id, c, ka, occupancy_only, occ);
-    case 2: return run_kernel<2, Dist>(id, c, ka, occupancy_only, occ);
-    case 4: return run_kernel<4, Dist>(id, c, ka, occupancy_only, occ);
-    case 8: return run_kernel<8, Dist>(id, c, ka, occupancy_only, occ);
-    case 16: return run_kernel<16, Dist>(id, c, ka, occupancy_only, occ);
-    case 32: return run_kernel<32, Dist>(id, c, ka, occupancy_only, occ);
+  if constexpr (PART == 0 || PART == 1) {
+    switch (efr) {
+      case 1: return run_kernel<1, Dist>(id, c, ka, occupancy_only, occ);
+      case 2: return run_kernel<2, Dist>(id, c, ka, occupancy_only, occ);
+      case 4: return run_kernel<4, Dist>(id, c, ka, occupancy_only, occ);
+    }
+  }
+  if constexpr (PART == 0 || PART == 2) {
+    switch (efr) {
+      case 8: return run_kernel<8, Dist>(id, c, ka, occupancy_only, occ);
+      case 16: return run_kernel<16, Dist>(id, c, ka, occupancy_only, occ);
+    }
+  }
+  if constexpr (PART == 0 || PART == 3) {
+    if (efr == 32) return run_kernel<32, Dist>(id, c, ka, occupancy_only, occ);
   }
   return cudaErrorInvalidValue;
 }
@@ -168,6 +178,27 @@ cudaError_t run_kind_scalar(int id, int efr, const LaunchCfg& c, const KernelArg
   cudaError_t run_kind_##NAME(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only,    \
                               int* occ) {                                                                        \
     return run_kind<DIST>(id, efr, c, ka, occupancy_only, occ);                                                  \
+  }                                                                                                              \
+  }
+// one part of a kind (see run_kind): defines run_kind_<NAME>_p<PART>
+#define HNSW_DEFINE_KIND_PART(NAME, DIST, PART)                                                                  \
+  namespace hnsw {                                                                                               \
+  cudaError_t run_kind_##NAME##_p##PART(int id, int efr, const LaunchCfg& c, const KernelArgs& ka,               \
+                                        bool occupancy_only, int* occ) {                                        \
+    return run_kind<DIST, PART>(id, efr, c, ka, occupancy_only, occ);                                            \
+  }                                                                                                              \
+  }
+// the kind's entry point when its classes are split over three translation units
+#define HNSW_DECLARE_KIND_PARTS(NAME)                                                                            \
+  namespace hnsw {                                                                                               \
+  cudaError_t run_kind_##NAME##_p1(int, int, const LaunchCfg&, const KernelArgs&, bool, int*);                  \
+  cudaError_t run_kind_##NAME##_p2(int, int, const LaunchCfg&, const KernelArgs&, bool, int*);                  \
+  cudaError_t run_kind_##NAME##_p3(int, int, const LaunchCfg&, const KernelArgs&, bool, int*);                  \
+  cudaError_t run_kind_##NAME(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, bool occupancy_only,    \
+                              int* occ) {                                                                        \
+    if (efr <= 4) return run_kind_##NAME##_p1(id, efr, c, ka, occupancy_only, occ);                              \
+    if (efr <= 16) return run_kind_##NAME##_p2(id, efr, c, ka, occupancy_only, occ);                             \
+    return run_kind_##NAME##_p3(id, efr, c, ka, occupancy_only, occ);                                            \
   }                                                                                                              \
   }
 

@@ -37,6 +37,7 @@ struct CandList {
     for (int r = 0; r < EFR; ++r) sim[r] = -CUDART_INF_F, id[r] = kEmpty;
     len = 0;
     worst = -CUDART_INF_F;
+    wpos = 0;
   }
 
   __device__ __forceinline__ bool admits(float s, int ef) const { return len < ef || s > worst; }  // core.rs:657
@@ -86,6 +87,159 @@ struct CandList {
       if (pos < 0 && b) pos = r * 32 + __ffs(b) - 1;
     }
     return pos;
+  }
+
+  // ---- WIDE mode (EFR >= 4, staged search kernels) ------------------------------------------------------------------
+  // Keeping the list sorted costs ~12 instructions per list register per admitted candidate (profiles/r1e_curve.md: the
+  // ef = 200 / 400 classes ran at 0.68 / 0.43 of the roofline because of it).  Nothing in search_level needs the order
+  // while the search runs — only the ef-th best value (core.rs:651,657), the nearest unexpanded entry (core.rs:631) and,
+  // at the end, the ranking.  So during a search the entries sit in arrival order; an admitted candidate overwrites the
+  // worst entry (one warp arg-min over EFR registers per lane), the next candidate is a warp arg-max over the unexpanded
+  // entries, and ONE bitonic sort at the end of the level restores the sorted layout every consumer of the list expects.
+  static constexpr bool kWide = EFR >= 4;
+  int wpos;          // wide mode: slot of the worst entry once len == ef (warp-uniform)
+
+  __device__ __forceinline__ void insert_wide(float s, uint32_t nid, int ef, int lane) {
+    const int slot = len < ef ? len : wpos;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r)
+      if (r == (slot >> 5) && lane == (slot & 31)) sim[r] = s, id[r] = nid;
+    if (len < ef) ++len;
+    if (len == ef) {                                           // the ef-th best value and where it sits
+      float m = CUDART_INF_F;
+      int mp = 0;
+#pragma unroll
+      for (int r = 0; r < EFR; ++r) {
+        const int e = r * 32 + lane;
+        if (e < ef && sim[r] < m) m = sim[r], mp = e;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float om = __shfl_xor_sync(kFull, m, off);
+        const int op = __shfl_xor_sync(kFull, mp, off);
+        if (om < m || (om == m && op > mp)) m = om, mp = op;
+      }
+      worst = m, wpos = mp;
+    }
+  }
+
+  // nearest unexpanded entry -> (nid, s), marked expanded; false if there is none (core.rs:631-638)
+  __device__ __forceinline__ bool pop_wide(uint32_t& nid, float& s, int lane) {
+    float b = -CUDART_INF_F;
+    int bp = -1;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) {
+      const bool open = id[r] != kEmpty && !(id[r] & kExpanded);
+      if (open && (bp < 0 || sim[r] > b)) b = sim[r], bp = r * 32 + lane;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(kFull, b, off);
+      const int op = __shfl_xor_sync(kFull, bp, off);
+      if (op >= 0 && (bp < 0 || ob > b || (ob == b && op < bp))) b = ob, bp = op;
+    }
+    if (bp < 0) return false;
+    uint32_t vi = kEmpty;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r)
+      if (r == (bp >> 5)) {
+        vi = id[r];
+        if (lane == (bp & 31)) id[r] |= kExpanded;
+      }
+    nid = __shfl_sync(kFull, vi, bp & 31) & ~kExpanded;
+    s = b;
+    return true;
+  }
+
+  // bitonic sort of the EFR * 32 slots into the sorted layout (entry of rank e in lane e % 32, register e / 32, nearest
+  // first; unused slots carry -inf and end up last)
+  __device__ __forceinline__ void sort_wide(int lane) {
+    constexpr int N = EFR * 32;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j >= 32; j >>= 1) {                 // partner in another register of the same lane (static indices)
+#pragma unroll
+        for (int r = 0; r < EFR; ++r) {
+          const int pr = r ^ (j >> 5);
+          if (pr > r) {
+            const bool desc = ((r * 32 + lane) & k) == 0;      // this block sorts descending
+            const bool swap = desc ? (sim[r] < sim[pr]) : (sim[r] > sim[pr]);
+            if (swap) {
+              const float ts = sim[r];
+              sim[r] = sim[pr], sim[pr] = ts;
+              const uint32_t ti = id[r];
+              id[r] = id[pr], id[pr] = ti;
+            }
+          }
+        }
+      }
+      // partner in another lane, same register: a run-time loop keeps the code small (the compile time of the fully
+      // unrolled network was 30 minutes for the library)
+#pragma unroll 1
+      for (int j = (k >> 1) < 16 ? (k >> 1) : 16; j > 0; j >>= 1) {
+        const bool lower = (lane & j) == 0;                    // the member of the pair with the smaller index
+#pragma unroll
+        for (int r = 0; r < EFR; ++r) {
+          const float os = __shfl_xor_sync(kFull, sim[r], j);
+          const uint32_t oi = __shfl_xor_sync(kFull, id[r], j);
+          const bool desc = ((r * 32 + lane) & k) == 0;
+          // descending block: the smaller index keeps the larger sim
+          const bool take = (desc == lower) ? (os > sim[r]) : (os < sim[r]);
+          if (take) sim[r] = os, id[r] = oi;
+        }
+      }
+    }
+  }
+
+  // ---- mode-independent interface used by the staged kernels
+  __device__ __forceinline__ void push(float s, uint32_t nid, int ef, int lane) {
+    if constexpr (kWide) insert_wide(s, nid, ef, lane);
+    else insert(s, nid, ef, lane);
+  }
+  __device__ __forceinline__ bool pop(uint32_t& nid, float& s, int lane) {
+    if constexpr (kWide) {
+      return pop_wide(nid, s, lane);
+    } else {
+      const int pos = first_unexpanded();
+      if (pos < 0) return false;
+      get(pos, lane, true, nid, s);
+      return true;
+    }
+  }
+  __device__ __forceinline__ void finish(int lane) {
+    if constexpr (kWide) sort_wide(lane);
+  }
+  // id of the nearest unexpanded entry without marking it (the lookahead's prediction, search_la.cuh)
+  __device__ __forceinline__ bool peek(uint32_t& nid, int lane) {
+    if constexpr (kWide) {
+      float b = -CUDART_INF_F;
+      int bp = -1;
+#pragma unroll
+      for (int r = 0; r < EFR; ++r) {
+        const bool open = id[r] != kEmpty && !(id[r] & kExpanded);
+        if (open && (bp < 0 || sim[r] > b)) b = sim[r], bp = r * 32 + lane;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(kFull, b, off);
+        const int op = __shfl_xor_sync(kFull, bp, off);
+        if (op >= 0 && (bp < 0 || ob > b || (ob == b && op < bp))) b = ob, bp = op;
+      }
+      if (bp < 0) return false;
+      uint32_t vi = kEmpty;
+#pragma unroll
+      for (int r = 0; r < EFR; ++r)
+        if (r == (bp >> 5)) vi = id[r];
+      nid = __shfl_sync(kFull, vi, bp & 31) & ~kExpanded;
+      return true;
+    } else {
+      const int pos = first_unexpanded();
+      if (pos < 0) return false;
+      float s;
+      get(pos, lane, false, nid, s);
+      return true;
+    }
   }
 
   // read entry `pos` (warp-uniform) and optionally mark it expanded

@@ -209,10 +209,10 @@ struct Recent<Way2> {
 
 template <int EFR>
 __device__ __forceinline__ bool list_has(const CandList<EFR>& L, uint32_t x) {
-  bool hit = false;
-#pragma unroll
-  for (int r = 0; r < EFR; ++r) hit |= __any_sync(kFull, L.id[r] != kEmpty && (L.id[r] & ~kExpanded) == x);
-  return hit;
+  bool hit = false;   // node ids are < 2^31, so an empty slot (0xFFFFFFFF) never equals x once the flag bit is masked... it
+#pragma unroll        // would equal 0x7FFFFFFF, which is not a node id either
+  for (int r = 0; r < EFR; ++r) hit |= (L.id[r] & ~kExpanded) == x;
+  return __any_sync(kFull, hit);
 }
 
 // ---------------------------------------------------------------- per-warp context
@@ -385,7 +385,7 @@ __device__ __forceinline__ void eval_and_admit(const Graph& g, Warp2<C, S, T>& w
       const float sj = __shfl_sync(kFull, s, j);
       const uint32_t idj = __shfl_sync(kFull, id, j);
       if (L.admits(sj, ef) && !list_has<EFR>(L, idj)) {          // core.rs:657 (threshold re-read per neighbour)
-        L.insert(sj, idj, ef, lane);                             // core.rs:658-664
+        L.push(sj, idj, ef, lane);                               // core.rs:658-664
         if (adj_prefetch && lane < (int)(g.W / 32)) prefetch_l2(adj_prefetch + (size_t)idj * g.W + lane * 32);
       }
     }
@@ -425,11 +425,9 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
     eval_and_admit<EFR, C, S, T, COPY>(g, w, nb, 1u, ef, L, adj_prefetch, lane);
   }
   for (;;) {
-    const int pos = L.first_unexpanded();                        // core.rs:631-638
-    if (pos < 0) break;
     uint32_t cid;
     float cs;
-    L.get(pos, lane, true, cid, cs);
+    if (!L.pop(cid, cs, lane)) break;                            // core.rs:631-638
     cnt.n_hops += 1;
     uint32_t* ovf;
     const uint32_t* row = row_ptr(g, cid, level, &ovf);          // core.rs:642-645
@@ -451,6 +449,7 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
       }
     }
   }
+  L.finish(lane);                                                // wide lists: back to the sorted layout (search.cuh)
 }
 
 // shared memory per warp (bytes), 128-byte aligned pieces: stage | visited | ids | mbarrier

@@ -20,6 +20,12 @@
 
 namespace hnsw {
 
+// Measured (r2 call G, 1M x 128, ef 64): one HNSW.SEARCH 211 us without / 224 us with the lookahead, a 1250-query slice
+// 450 / 476 us, SPEC K1 unchanged — a hop is bound by its ~1100 dependent instructions (list maintenance, shuffles,
+// ballots), not by the two memory round trips the lookahead overlaps (profiles/r2_latency.md).  The kernel stays behind
+// the `lookahead` option (default off) as the record of that experiment; the builders do not use it.
+constexpr bool kLookaheadInBuilders = false;
+
 template <int C>
 struct LaBuf {
   const float* stage[2];   // [32][32 * C] floats each
@@ -94,7 +100,7 @@ __device__ __forceinline__ void la_finish(const Graph& g, const float (&q)[C], c
     const float sj = __shfl_sync(kFull, s, j);
     const uint32_t idj = __shfl_sync(kFull, id, j);
     if (L.admits(sj, ef) && !list_has<EFR>(L, idj)) {          // core.rs:657 (threshold re-read per neighbour)
-      L.insert(sj, idj, ef, lane);                             // core.rs:658-664
+      L.push(sj, idj, ef, lane);                               // core.rs:658-664
       if (adj_prefetch && lane < (int)(g.W / 32)) prefetch_l2(adj_prefetch + (size_t)idj * g.W + lane * 32);
     }
   }
@@ -119,11 +125,9 @@ __device__ __forceinline__ void search_layer2_la(const Graph& g, Warp2<C, S, T>&
   uint32_t pf_cid = kEmpty, pf_nb = kEmpty, pf_mask = 0, pf_vcnt = 0;
   int pf_buf = 0;
   for (;;) {
-    const int pos = L.first_unexpanded();                        // core.rs:631-638
-    if (pos < 0) break;
     uint32_t cid;
     float cs;
-    L.get(pos, lane, true, cid, cs);
+    if (!L.pop(cid, cs, lane)) break;                            // core.rs:631-638
     cnt.n_hops += 1;
     uint32_t* ovf;
     const uint32_t* row = row_ptr(g, cid, level, &ovf);          // core.rs:642-645
@@ -152,11 +156,8 @@ __device__ __forceinline__ void search_layer2_la(const Graph& g, Warp2<C, S, T>&
     const int n_new = __popc(newmask);
     cnt.n_dist += n_new;                                         // core.rs:652-656
     if (!more) {                                                 // lookahead: the nearest unexpanded entry as the list stands now
-      const int p = L.first_unexpanded();
-      if (p >= 0) {
-        uint32_t pid;
-        float ps;
-        L.get(p, lane, false, pid, ps);
+      uint32_t pid = kEmpty;
+      if (L.peek(pid, lane)) {
         uint32_t* povf;
         const uint32_t* prow = row_ptr(g, pid, level, &povf);
         if (prow) {
@@ -196,6 +197,7 @@ __device__ __forceinline__ void search_layer2_la(const Graph& g, Warp2<C, S, T>&
     }
   }
   if (pf_valid) cp_async_wait_all();                             // nothing may still be landing when the stages are reused
+  L.finish(lane);
 }
 
 // core.rs:477-486, 865-892 — search_knn2_kernel's latency flavour: 32-row stage, cp.async rows, one-hop lookahead.

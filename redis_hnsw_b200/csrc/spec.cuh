@@ -207,6 +207,7 @@ __device__ __forceinline__ void reprune_select2v(const Graph& g, SpecLog& lg, Wa
     for (uint32_t i = 0; i < n_row; i += 32) feed((i + lane < n_row) ? tmp[i + lane] : kEmpty);
   }
   if (np) flush(np);
+  L.finish(lane);                                                // wide lists (EFR >= 4): back to the sorted layout
 }
 
 // ---------------------------------------------------------------- K1
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
 
   Warp2<C, S, T> w;
   unsigned char* after = warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane);
-  constexpr bool kLookahead = S == 32 && RowCopy<C>::kOk;          // search_la.cuh: second stage for the next hop's rows
+  constexpr bool kLookahead = kLookaheadInBuilders && S == 32 && RowCopy<C>::kOk;          // search_la.cuh: second stage for the next hop's rows
   LaBuf<C> lb;
   if constexpr (kLookahead) after = la_setup<C, S, T>(lb, w, after, lane);
   uint32_t* lists = reinterpret_cast<uint32_t*>(after);

@@ -30,7 +30,8 @@ def main():
     wl = args.workload
     n, dim, m, efc, ds, r_lat = bench.WORKLOADS[wl]
     x, q, levels = bench.make_data(wl, args.nq)
-    dev, build_s = bench.build_index(wl, x, levels, 0, 0, 1)
+    dev, _binfo = bench.build_index(wl, x, levels, 0, 0, 1)
+    build_s = _binfo["build_seconds"]
     gt = data.brute_force_topk(x, q[:2000], 10, device="cuda")
     d_q = torch.from_numpy(q).cuda()
     nq = args.nq

@@ -31,7 +31,8 @@ def main():
     wl = args.workload
     n, dim, m, efc, _, _ = bench.WORKLOADS[wl]
     x, q, levels = bench.make_data(wl, args.nq)
-    dev, build_s = bench.build_index(wl, x, levels, 0, 0, 1)
+    dev, _binfo = bench.build_index(wl, x, levels, 0, 0, 1)
+    build_s = _binfo["build_seconds"]
     nq, k = args.nq, 10
     d_q = torch.from_numpy(q).cuda()
     d_ids = torch.empty((nq, k), dtype=torch.int32, device="cuda")
