@@ -44,6 +44,8 @@ def lib():
         L.orc_cut_ties_reset.argtypes = []
         L.orc_evict_ties.restype = C.c_uint64
         L.orc_evict_ties.argtypes = []
+        L.orc_order_ties.restype = C.c_uint64
+        L.orc_order_ties.argtypes = []
         L.orc_level_from_u.restype = C.c_int
         L.orc_level_from_u.argtypes = [C.c_double, C.c_int]
         L.orc_add.restype = C.c_int64
@@ -111,10 +113,11 @@ def euclidean_batch(a, b):
 
 
 def cut_ties(reset=False):
-    """(select ties, eviction ties) since the last reset (process-wide): equal sims of different nodes on either side of a
-    cut — the m-th / (m+1)-th candidate of select_neighbors, the two worst of w at an eviction — i.e. outcomes the reference
-    leaves to BinaryHeap internals.  Parity fixtures are chosen so that the first is 0."""
-    n = (int(lib().orc_cut_ties()), int(lib().orc_evict_ties()))
+    """(select ties, eviction ties, order ties) since the last reset (process-wide): equal sims of different nodes on either
+    side of a cut — the m-th / (m+1)-th candidate of select_neighbors, the two worst of w at an eviction — i.e. outcomes the
+    reference leaves to BinaryHeap internals; and equal sims among the SELECTED candidates, where the set is pinned but the
+    order of the tied pair in the adjacency list is not.  Parity fixtures are chosen so that the first is 0."""
+    n = (int(lib().orc_cut_ties()), int(lib().orc_evict_ties()), int(lib().orc_order_ties()))
     if reset:
         lib().orc_cut_ties_reset()
     return n

@@ -66,6 +66,7 @@ thread_local Stats* g_stats = nullptr;
 // There the reference's outcome is decided by BinaryHeap internals; parity fixtures are chosen so that this stays 0
 // (tests/golden/make_graph_fingerprint.py).  Diagnostic only: no behaviour depends on it.
 std::atomic<uint64_t> g_cut_ties{0};     // select_neighbors: m-th and (m+1)-th candidate tie
+std::atomic<uint64_t> g_order_ties{0};   // select_neighbors: two SELECTED candidates tie (the set is fixed, their order in the list is not)
 std::atomic<uint64_t> g_evict_ties{0};   // search_level: the two worst members of w tie at an eviction (almost always harmless:
                                          // both sit at the far edge of an early, wide w and are evicted shortly after)
 
@@ -426,6 +427,13 @@ struct Oracle {
       for (const MaxHeap* rest : {&wd, &w})
         for (const Pair& p : rest->data)
           if (p.id != query && p.id != ignored && of_cmp(p.sim, worst) == 0) tie = true;
+      {  // equal sims among the selected: the result SET is pinned, the list order of the tied pair is a heap accident
+        std::vector<float> ss;
+        for (const Pair& p : r.data) ss.push_back(p.sim);
+        std::sort(ss.begin(), ss.end());
+        for (size_t i = 1; i < ss.size(); ++i)
+          if (of_cmp(ss[i], ss[i - 1]) == 0) g_order_ties++;
+      }
       if (tie) {
         g_cut_ties++;
         if (getenv("ORC_TIE_DEBUG")) fprintf(stderr, "select tie: query=%u mm=%zu lc=%d worst=%g |w|=%zu |wd|=%zu\n", query, mm, lc, worst, w.len(), wd.len());
@@ -638,7 +646,8 @@ void orc_euclidean_batch(const float* a, const float* b, uint64_t n, uint64_t di
 
 uint64_t orc_cut_ties() { return g_cut_ties.load(); }
 uint64_t orc_evict_ties() { return g_evict_ties.load(); }
-void orc_cut_ties_reset() { g_cut_ties = 0, g_evict_ties = 0; }
+uint64_t orc_order_ties() { return g_order_ties.load(); }
+void orc_cut_ties_reset() { g_cut_ties = 0, g_evict_ties = 0, g_order_ties = 0; }
 
 int orc_level_from_u(double u, int m) { return Oracle::level_from_u(u, 1.0 / std::log((double)m)); }
 

@@ -76,6 +76,7 @@ struct Index {
   uint32_t* d_ver0 = nullptr;     // [cap_nodes] SPEC builder row stamps: 1 + id of the last insert that wrote the row
   uint32_t* d_verU = nullptr;     // [cap_upper]
   uint32_t opt_spec_window = 0;   // SPEC: fixed window size (0 = adaptive)
+  uint32_t opt_spec_mult = 0;     // SPEC: adaptive window = mult / 10 x (inserts committed per round, running mean); 0 = 40
 
   // scratch
   Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis, s_spec;

@@ -96,7 +96,12 @@ struct CandList {
   // at the end, the ranking.  So during a search the entries sit in arrival order; an admitted candidate overwrites the
   // worst entry (one warp arg-min over EFR registers per lane), the next candidate is a warp arg-max over the unexpanded
   // entries, and ONE bitonic sort at the end of the level restores the sorted layout every consumer of the list expects.
-  static constexpr bool kWide = EFR >= 4;
+  // MEASURED (r2 call H, 1M x 128): slower, not faster — ef 96 / 200 / 400 ran at 3.5 / 2.0 / 1.0 TB/s algorithmic against
+  // 6.0 / 4.5 / 2.8 TB/s for the sorted list.  The sorted insert is cheaper than it looks (registers before the insert
+  // position are skipped, its ballots and shifts are independent), while the arg-min / arg-max butterflies are dependent
+  // shuffle chains, and under the register caps of Search2Bounds the sort's swaps spill (2.3 KB at EFR = 16).  The mode is
+  // kept compiled out as the record of the experiment (profiles/r2_experiments.md).
+  static constexpr bool kWide = false;
   int wpos;          // wide mode: slot of the worst entry once len == ef (warp-uniform)
 
   __device__ __forceinline__ void insert_wide(float s, uint32_t nid, int ef, int lane) {

@@ -6,8 +6,9 @@ GPU test, so its graph is pinned here once.
 
     python tests/golden/make_graph_fingerprint.py        # ~6 min on one core; writes graph_fingerprint_100k.json
 
-The fingerprint holds sha256 of the exported arrays (levels, row offsets, neighbour ids, enterpoint, max_layer), the
-same for every prefix checkpoint of `checkpoints` nodes (so a mismatch is localised), and a few literal adjacency lists.
+The fingerprint holds, for every prefix checkpoint: sha256 of the exported arrays (levels, row offsets, neighbour ids,
+enterpoint, max_layer) in list order, the same with every list taken as a set, order-sensitive digests of every block of
+1000 rows (a mismatch is localised), the oracle's tie counters, and a few literal adjacency lists.
 """
 import hashlib
 import json
@@ -30,13 +31,41 @@ DATA_SEED = int(os.environ.get("FP_DATA_SEED", "126"))
 LEVEL_SEED = 42
 
 
-def graph_digest(g):
+def _rows(g):
+    offs = np.ascontiguousarray(g["row_offs"], np.uint64)
+    nbrs = np.ascontiguousarray(g["nbrs"], np.uint32)
+    return offs, nbrs
+
+
+def graph_digest(g, as_sets=False):
+    """sha256 of the exported graph.  as_sets = True hashes every adjacency list as a SET (ids ascending): two graphs that
+    differ only in the order of neighbours whose sims tie exactly (the reference leaves that order to
+    BinaryHeap internals) have the same set digest."""
+    offs, nbrs = _rows(g)
+    if as_sets:
+        nbrs = nbrs.copy()
+        row_of = np.repeat(np.arange(offs.size - 1, dtype=np.int64), np.diff(offs).astype(np.int64))
+        order = np.lexsort((nbrs, row_of))
+        nbrs = nbrs[order]
     h = hashlib.sha256()
     h.update(np.ascontiguousarray(g["levels"], np.int32).tobytes())
-    h.update(np.ascontiguousarray(g["row_offs"], np.uint64).tobytes())
-    h.update(np.ascontiguousarray(g["nbrs"], np.uint32).tobytes())
+    h.update(offs.tobytes())
+    h.update(nbrs.tobytes())
     h.update(np.array([g["entry"], g["max_layer"]], np.int64).tobytes())
     return h.hexdigest()
+
+
+def block_digests(g, block=1000):
+    """Order-sensitive digest of every block of `block` adjacency rows (16 hex digits each): localises a difference."""
+    offs, nbrs = _rows(g)
+    out = []
+    for r0 in range(0, offs.size - 1, block):
+        r1 = min(offs.size - 1, r0 + block)
+        h = hashlib.sha256()
+        h.update((offs[r0:r1 + 1] - offs[r0]).tobytes())
+        h.update(nbrs[int(offs[r0]):int(offs[r1])].tobytes())
+        out.append(h.hexdigest()[:16])
+    return out
 
 
 def dataset():
@@ -65,7 +94,9 @@ def main():
         done = cp
         g = orc.export_graph()
         deg0 = np.diff(g["row_offs"])
-        out["checkpoints"][str(cp)] = {"sha256": graph_digest(g), "edges": int(g["nbrs"].size), "rows": int(deg0.size),
+        out["checkpoints"][str(cp)] = {"sha256": graph_digest(g), "set_sha256": graph_digest(g, as_sets=True),
+                                       "row_blocks": block_digests(g), "order_ties": oracle.cut_ties()[2],
+                                       "edges": int(g["nbrs"].size), "rows": int(deg0.size),
                                        "max_degree": int(deg0.max()), "entry": g["entry"], "max_layer": g["max_layer"],
                                        # equal sims of different nodes across a cut so far: (select_neighbors, w evictions)
                                        "select_ties": oracle.cut_ties()[0], "evict_ties": oracle.cut_ties()[1]}

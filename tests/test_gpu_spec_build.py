@@ -116,6 +116,7 @@ def test_spec_build_100k_matches_the_oracle_fingerprint():
     dev = r.DeviceIndex(fp.DIM, fp.M, fp.EFC)
     dev.reserve(fp.N)
     done = 0
+    order_only = []
     for cp in fp.CHECKPOINTS:
         dev.add_batch(x[done:cp], levels[done:cp], mode=r.BUILD_SPEC)
         done = cp
@@ -123,9 +124,18 @@ def test_spec_build_100k_matches_the_oracle_fingerprint():
         want = gold["checkpoints"][str(cp)]
         assert g["nbrs"].size == want["edges"], "edge count differs at %d nodes" % cp
         assert (g["entry"], g["max_layer"]) == (want["entry"], want["max_layer"])
-        assert fp.graph_digest(g) == want["sha256"], "graph differs from the oracle's at %d nodes" % cp
+        # every adjacency list holds the oracle's neighbours ...
+        assert fp.graph_digest(g, as_sets=True) == want["set_sha256"], "graph differs from the oracle's at %d nodes" % cp
+        # ... in the oracle's order, except where two SELECTED neighbours tie exactly: the reference leaves the order of such
+        # a pair to BinaryHeap internals.  The oracle counts those ties; a row block may differ only if
+        # there are any, and never more blocks than ties (r2: rows 58514 and 58931 — sims -40.496078 and -42.798759 twice).
+        if fp.graph_digest(g) != want["sha256"]:
+            diff = sum(a != b for a, b in zip(fp.block_digests(g), want["row_blocks"]))
+            assert 0 < diff <= want["order_ties"], "%d row blocks differ in order at %d nodes (%d order ties)" % (
+                diff, cp, want["order_ties"])
+            order_only.append((cp, diff))
     for i, lst in gold["sample_lists"].items():
-        assert [int(v) for v in dev.node_neighbors(int(i), 0)] == lst
+        assert sorted(int(v) for v in dev.node_neighbors(int(i), 0)) == sorted(lst)
     st = dev.build_stats()
     assert st["inserts"] == fp.N - 1
-    print("SPEC 100k: %s" % st)
+    print("SPEC 100k: %s; checkpoints equal as sets everywhere, order differs (tied pairs) in %s" % (st, order_only))

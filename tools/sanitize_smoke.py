@@ -13,7 +13,8 @@ for dim, m, efc in ((128, 16, 64), (32, 5, 40), (20, 6, 32), (96, 8, 32)):
     lv = data.draw_levels(n, m, seed=2)
     a = r.l2_batch(x[:256], x[256:512])
     dev = r.DeviceIndex(dim, m, efc)
-    dev.add_batch(x[:600], lv[:600], mode=r.BUILD_EXACT)
+    dev.add_batch(x[:400], lv[:400], mode=r.BUILD_EXACT)
+    dev.add_batch(x[400:600], lv[400:600], mode=r.BUILD_SPEC)      # r2: speculative-exact windows (spec_exec / spec_commit)
     dev.add_batch(x[600:], lv[600:], mode=r.BUILD_FAST)
     for i in range(5):
         dev.add(q[i], -1)
@@ -25,6 +26,12 @@ for dim, m, efc in ((128, 16, 64), (32, 5, 40), (20, 6, 32), (96, 8, 32)):
         ib, sb, cb = dev.search_batch(big, 10, ef=48)
         assert np.array_equal(ib[:64], ids) and np.array_equal(ib[-64:], ids)
     dev.search(q[0], 5)
+    if dim in (128, 32):                                            # r2: one query per CTA, lookahead kernel (options)
+        for opt in ("search_cta", "lookahead"):
+            dev.set_option(opt, 1)
+            i3, s3, c3 = dev.search_batch(q[:8], 10, ef=48)
+            assert np.array_equal(i3, ids[:8])
+            dev.set_option(opt, 0)
     dev.search_level(q[0], int(dev.params()["enterpoint"]), 8, 0)
     for v in (3, 700, int(dev.params()["enterpoint"]), 1499):
         dev.delete(v)
