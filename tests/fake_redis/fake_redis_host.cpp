@@ -128,22 +128,104 @@ static void add_reply(Ctx* c, Reply r) {
 }
 
 // ---- RDB-style typed IO
+// Module values are serialised with redis-server's own RDB encoding for module types (rdb.c, RDB_TYPE_MODULE_2), so a
+// payload written here is byte for byte what `hnsw.{index}` / `hnsw.{index}.{node}` hold inside a real dump.rdb — and a
+// payload derived by hand from the reference's rdb_save callbacks (tests/golden/make_rdb_fixture.py) loads here:
+//   value   := len(module id) item* len(0 = RDB_MODULE_OPCODE_EOF)
+//   item    := len(2 = UINT) len(v) | len(3 = FLOAT) 4 bytes LE | len(4 = DOUBLE) 8 bytes LE | len(5 = STRING) string
+//   len(v)  := 00vvvvvv | 01vvvvvv vvvvvvvv | 0x80 u32 big-endian | 0x81 u64 big-endian                    (rdbSaveLen)
+//   string  := len(n) n bytes | 0xC0 int8 | 0xC1 int16 LE | 0xC2 int32 LE | 0xC3 len(clen) len(ulen) LZF bytes
+//              (rdbSaveRawString: this host always WRITES the first form — what redis-server writes for strings that do not
+//              look like integers and are <= 20 bytes, or with `rdbcompression no` — and READS all of them)
+//   module id = 9 name characters, 6 bits each (A-Za-z0-9-_), then 10 bits of encoding version         (moduleTypeEncodeId)
+enum { kOpEof = 0, kOpSint = 1, kOpUint = 2, kOpFloat = 3, kOpDouble = 4, kOpString = 5 };
+
+static void rdb_put_len(std::string& b, uint64_t v) {
+  if (v < (1u << 6)) {
+    b.push_back((char)v);
+  } else if (v < (1u << 14)) {
+    b.push_back((char)(0x40 | (v >> 8)));
+    b.push_back((char)(v & 0xFF));
+  } else if (v <= 0xFFFFFFFFull) {
+    b.push_back((char)0x80);
+    for (int i = 3; i >= 0; --i) b.push_back((char)((v >> (8 * i)) & 0xFF));
+  } else {
+    b.push_back((char)0x81);
+    for (int i = 7; i >= 0; --i) b.push_back((char)((v >> (8 * i)) & 0xFF));
+  }
+}
+
+// returns false at the end of the buffer or on a special ("encoded") length, whose kind is stored in *enc
+static bool rdb_get_len(const std::string& b, size_t& pos, uint64_t* v, int* enc = nullptr) {
+  if (enc) *enc = -1;
+  if (pos >= b.size()) return false;
+  const unsigned char c = (unsigned char)b[pos++];
+  const int type = c >> 6;
+  if (type == 0) {
+    *v = c & 0x3F;
+  } else if (type == 1) {
+    if (pos >= b.size()) return false;
+    *v = ((uint64_t)(c & 0x3F) << 8) | (unsigned char)b[pos++];
+  } else if (c == 0x80 || c == 0x81) {
+    const int n = c == 0x80 ? 4 : 8;
+    if (pos + n > b.size()) return false;
+    *v = 0;
+    for (int i = 0; i < n; ++i) *v = (*v << 8) | (unsigned char)b[pos++];
+  } else {
+    if (enc) *enc = c & 0x3F;  // 11xxxxxx: specially encoded string
+    return false;
+  }
+  return true;
+}
+
+static const char* kModuleIdChars = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_";
+static uint64_t module_type_id(const std::string& name, int encver) {
+  uint64_t id = 0;
+  for (int i = 0; i < 9; ++i) {
+    const char* p = std::strchr(kModuleIdChars, i < (int)name.size() ? name[i] : 'A');
+    id = (id << 6) | (uint64_t)(p ? p - kModuleIdChars : 0);
+  }
+  return (id << 10) | (uint64_t)(encver & 1023);
+}
+
+// liblzf decompression (the format rdbSaveLzfStringObject writes)
+static bool lzf_decompress(const unsigned char* in, size_t in_len, std::string* out, size_t out_len) {
+  size_t ip = 0;
+  out->clear();
+  while (ip < in_len) {
+    unsigned ctrl = in[ip++];
+    if (ctrl < 32) {
+      ctrl++;
+      if (ip + ctrl > in_len) return false;
+      out->append((const char*)in + ip, ctrl);
+      ip += ctrl;
+    } else {
+      size_t len = ctrl >> 5;
+      if (len == 7) {
+        if (ip >= in_len) return false;
+        len += in[ip++];
+      }
+      if (ip >= in_len) return false;
+      const size_t ref_off = ((size_t)(ctrl & 0x1F) << 8) + in[ip++] + 1;
+      if (ref_off > out->size()) return false;
+      size_t ref = out->size() - ref_off;
+      for (size_t i = 0; i < len + 2; ++i) out->push_back((*out)[ref + i]);
+    }
+  }
+  return out->size() == out_len;
+}
+
 struct IO {
   std::string buf;
   size_t pos = 0;
   bool error = false;
-  void put(char tag, const void* p, size_t n) {
-    buf.push_back(tag);
-    buf.append((const char*)p, n);
-  }
-  bool get(char tag, void* p, size_t n) {
-    if (pos + 1 + n > buf.size() || buf[pos] != tag) {
+  void op(int opcode) { rdb_put_len(buf, (uint64_t)opcode); }
+  bool expect(int opcode) {
+    uint64_t got = 0;
+    if (!rdb_get_len(buf, pos, &got) || got != (uint64_t)opcode) {
       error = true;
-      std::memset(p, 0, n);
       return false;
     }
-    std::memcpy(p, buf.data() + pos + 1, n);
-    pos += 1 + n;
     return true;
   }
 };
@@ -294,41 +376,86 @@ static int api_ReplyWithNull(void* ctx) {
   return 0;
 }
 
-static void api_SaveUnsigned(IO* io, uint64_t v) { io->put('U', &v, 8); }
+static void api_SaveUnsigned(IO* io, uint64_t v) {
+  io->op(kOpUint);
+  rdb_put_len(io->buf, v);
+}
 static uint64_t api_LoadUnsigned(IO* io) {
-  uint64_t v;
-  io->get('U', &v, 8);
+  uint64_t v = 0;
+  if (!io->expect(kOpUint) || !rdb_get_len(io->buf, io->pos, &v)) io->error = true;
   return v;
 }
-static void api_SaveDouble(IO* io, double v) { io->put('D', &v, 8); }
+static void api_SaveDouble(IO* io, double v) {
+  io->op(kOpDouble);
+  io->buf.append((const char*)&v, 8);  // rdbSaveBinaryDoubleValue: IEEE 754, little-endian
+}
 static double api_LoadDouble(IO* io) {
-  double v;
-  io->get('D', &v, 8);
+  double v = 0;
+  if (!io->expect(kOpDouble) || io->pos + 8 > io->buf.size()) {
+    io->error = true;
+    return 0;
+  }
+  std::memcpy(&v, io->buf.data() + io->pos, 8);
+  io->pos += 8;
   return v;
 }
-static void api_SaveFloat(IO* io, float v) { io->put('F', &v, 4); }
+static void api_SaveFloat(IO* io, float v) {
+  io->op(kOpFloat);
+  io->buf.append((const char*)&v, 4);  // rdbSaveBinaryFloatValue
+}
 static float api_LoadFloat(IO* io) {
-  float v;
-  io->get('F', &v, 4);
+  float v = 0;
+  if (!io->expect(kOpFloat) || io->pos + 4 > io->buf.size()) {
+    io->error = true;
+    return 0;
+  }
+  std::memcpy(&v, io->buf.data() + io->pos, 4);
+  io->pos += 4;
   return v;
 }
 static void api_SaveStringBuffer(IO* io, const char* p, size_t n) {
-  uint64_t len = n;
-  io->put('S', &len, 8);
+  io->op(kOpString);
+  rdb_put_len(io->buf, n);
   io->buf.append(p, n);
 }
 static char* api_LoadStringBuffer(IO* io, size_t* lenptr) {
+  std::string s;
   uint64_t len = 0;
-  if (!io->get('S', &len, 8) || io->pos + len > io->buf.size()) {
+  int enc = -1;
+  bool ok = io->expect(kOpString);
+  if (ok) {
+    if (rdb_get_len(io->buf, io->pos, &len, &enc)) {
+      ok = io->pos + len <= io->buf.size();
+      if (ok) s.assign(io->buf, io->pos, len), io->pos += len;
+    } else if (enc >= 0 && enc <= 2) {           // RDB_ENC_INT8 / INT16 / INT32: the string is the decimal of the integer
+      const size_t n = (size_t)1 << enc;
+      ok = io->pos + n <= io->buf.size();
+      if (ok) {
+        int64_t v = 0;
+        if (n == 1) v = (int8_t)io->buf[io->pos];
+        else if (n == 2) { int16_t t; std::memcpy(&t, io->buf.data() + io->pos, 2); v = t; }
+        else { int32_t t; std::memcpy(&t, io->buf.data() + io->pos, 4); v = t; }
+        io->pos += n;
+        s = std::to_string(v);
+      }
+    } else if (enc == 3) {                       // RDB_ENC_LZF
+      uint64_t clen = 0, ulen = 0;
+      ok = rdb_get_len(io->buf, io->pos, &clen) && rdb_get_len(io->buf, io->pos, &ulen) && io->pos + clen <= io->buf.size() &&
+           lzf_decompress((const unsigned char*)io->buf.data() + io->pos, clen, &s, ulen);
+      if (ok) io->pos += clen;
+    } else {
+      ok = false;
+    }
+  }
+  if (!ok) {
     io->error = true;
     if (lenptr) *lenptr = 0;
     return nullptr;
   }
-  char* out = (char*)std::malloc(len + 1);
-  std::memcpy(out, io->buf.data() + io->pos, len);
-  out[len] = 0;
-  io->pos += len;
-  if (lenptr) *lenptr = len;
+  char* out = (char*)std::malloc(s.size() + 1);
+  std::memcpy(out, s.data(), s.size());
+  out[s.size()] = 0;
+  if (lenptr) *lenptr = s.size();
   return out;
 }
 
@@ -439,10 +566,10 @@ static long long save_all(const std::string& path) {
   for (auto& kv : H.keys) {
     if (!kv.second.type) continue;
     IO io;
+    rdb_put_len(io.buf, module_type_id(kv.second.type->name, kv.second.type->encver));   // rdbSaveObject, RDB_TYPE_MODULE_2
     kv.second.type->m.rdb_save(&io, kv.second.value);
+    io.op(kOpEof);
     put_s(out, kv.first);
-    put_s(out, kv.second.type->name);
-    put_u64(out, (uint64_t)kv.second.type->encver);
     put_s(out, io.buf);
   }
   std::ofstream f(path, std::ios::binary);
@@ -490,22 +617,26 @@ static Reply meta(const std::vector<std::string>& w) {
     bool ok = take_u64(in, pos, &n);
     long long loaded = 0;
     for (uint64_t i = 0; ok && i < n; ++i) {
-      std::string key, type, payload;
-      uint64_t encver = 0;
-      ok = take_s(in, pos, &key) && take_s(in, pos, &type) && take_u64(in, pos, &encver) && take_s(in, pos, &payload);
+      std::string key, payload;
+      ok = take_s(in, pos, &key) && take_s(in, pos, &payload);
       if (!ok) break;
-      auto it = H.types.find(type);
-      if (it == H.types.end()) {
-        ok = false;
-        break;
-      }
       IO io;
       io.buf = payload;
-      void* v = it->second->m.rdb_load(&io, (int)encver);
-      if (!v || io.error || io.pos != io.buf.size()) {
+      uint64_t mid = 0;
+      ok = rdb_get_len(io.buf, io.pos, &mid);   // the module type id names the data type and its encoding version
+      RedisModuleType* mt = nullptr;
+      for (auto& t : H.types)
+        if (ok && (module_type_id(t.second->name, 0) >> 10) == (mid >> 10)) mt = t.second;
+      if (!mt) {
         ok = false;
         break;
       }
+      void* v = mt->m.rdb_load(&io, (int)(mid & 1023));
+      if (!v || io.error || !io.expect(kOpEof) || io.pos != io.buf.size()) {
+        ok = false;
+        break;
+      }
+      auto it = H.types.find(mt->name);
       drop_key(key);
       H.keys[key] = Entry{it->second, v};
       ++loaded;

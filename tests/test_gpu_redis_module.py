@@ -208,3 +208,33 @@ def test_node_madd_bulk_load(tmp_path, fast, events):
     if fast == 0:                                                  # same levels, same order -> same graph as one-by-one
         one = R.run(_build_cmds("idx", x, m, efc) + probe, env=env)
         assert one[n + 1:] == r[6:]
+
+
+def test_hand_derived_reference_rdb_loads_into_the_engine():
+    """The reference-format payloads of tests/golden/rdb_5node.fake_rdb (derived by hand from types.rs:243-284, 410-428, see
+    tests/golden/make_rdb_fixture.py) rebuild a working device index: the lazy rebuild of lib.rs:229-315 from records this
+    repo did not write.  core_tests.rs:45-53 in miniature: the nearest neighbours of [2;4] are n2 (sim -0), then n1 / n3
+    (sim -4 each)."""
+    import os
+
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rdb_5node.fake_rdb")
+    r = R.run(["#LOAD " + fixture, "HNSW.GET kat5", "HNSW.SEARCH kat5 K 3 QUERY 4 2 2 2 2", "HNSW.GET empty",
+               "HNSW.SEARCH empty K 3 QUERY 8 0 0 0 0 0 0 0 0", "HNSW.NODE.ADD kat5 n5 DATA 4 5 5 5 5", "HNSW.GET kat5",
+               "HNSW.NODE.GET kat5 n5", "HNSW.NODE.ADD empty first DATA 8 1 1 1 1 1 1 1 1", "HNSW.GET empty"])
+    assert r[0] == 7
+    g = R.pairs(r[1])
+    assert (g["name"], g["metric"], g["data_dim"], g["m"], g["ef_construction"], g["node_count"], g["max_layer"], g["enterpoint"]) == \
+        ("hnsw.kat5", "Euclidean", 4, 5, 16, 5, 1, "hnsw.kat5.n2")
+    assert r[2][0] == 3
+    hits = [R.pairs(x) for x in r[2][1:]]
+    assert [h["similarity"] for h in hits] == [-0.0, -4.0, -4.0] and hits[0]["name"] == "n2"
+    assert {hits[1]["name"], hits[2]["name"]} == {"n1", "n3"}
+    e = R.pairs(r[3])
+    assert (e["node_count"], e["max_layer"], e["enterpoint"]) == (0, 0, None)      # "null" (types.rs:234-237, 277-283)
+    assert r[4] == [0]                                                               # core.rs:481-483
+    assert r[5] == {"status": "OK"} and R.pairs(r[6])["node_count"] == 6
+    rec = R.pairs(r[7])
+    assert rec["data"] == [5.0] * 4 and set(rec["neighbors"][0]) == {"hnsw.kat5.n%d" % i for i in range(5)}
+    assert r[8] == {"status": "OK"}
+    e2 = R.pairs(r[9])
+    assert (e2["node_count"], e2["enterpoint"]) == (1, "hnsw.empty.first")
