@@ -212,10 +212,7 @@ __device__ __forceinline__ void row_remove(const Graph& g, uint32_t node, uint32
 // is `x` (warp-uniform) one of the entries of L?
 template <int EFR>
 __device__ __forceinline__ bool cand_contains(const CandList<EFR>& L, uint32_t x) {
-  bool hit = false;
-#pragma unroll
-  for (int r = 0; r < EFR; ++r) hit |= __any_sync(kFull, (L.id[r] & ~kExpanded) == x && L.id[r] != kEmpty);
-  return hit;
+  return L.contains(x, lane_id());
 }
 
 // expand_chunk with a LOSSY visited table (direct-mapped, most recent id per slot): a hit proves "already
@@ -323,12 +320,7 @@ __device__ __forceinline__ void reprune_delta(const CandList<EFR>& L, const uint
   }
   __syncwarp();
   for (int p = 0; p < L.len; ++p) {
-    uint32_t x = kEmpty;
-    int rr = p >> 5, l = p & 31;
-#pragma unroll
-    for (int r = 0; r < EFR; ++r)
-      if (r == rr) x = L.id[r];
-    x = __shfl_sync(kFull, x, l) & ~kExpanded;
+    const uint32_t x = L.entry_at(p, lane);
     if (list_find(old, n_old, x, lane) < 0) {
       if (lane == 0) keep_add[n_keep + n_add] = x;
       ++n_add;
@@ -348,6 +340,8 @@ struct ExactArgs {
   uint32_t* ctl;
   uint32_t* touched;       // optional: ids reported through update_fn (core.rs:580-584), duplicates allowed
   uint32_t touched_cap;
+  uint32_t* list_mem;      // CandList<0> (ef_construction or 2m beyond the register classes): [2 * list_cap] words
+  uint32_t list_cap;
 };
 
 template <int EFR, class Dist>
@@ -370,6 +364,7 @@ __global__ void __launch_bounds__(32) insert_exact_kernel(Graph g, ExactArgs a) 
 
   Dist dist;
   CandList<EFR> L;
+  L.bind(a.list_mem, a.list_cap);
   Counters cnt = {0, 0, 0};
   uint32_t n_touched = 0, n_reprunes = 0;
   auto touch = [&](uint32_t id) {
@@ -399,21 +394,13 @@ __global__ void __launch_bounds__(32) insert_exact_kernel(Graph g, ExactArgs a) 
       // because w was full, and the reference's sweep (core.rs:698-721) picks them up until m are selected.
       if (a.efc < a.m && (uint32_t)L.len == a.efc) {
         const uint32_t n_w = (uint32_t)L.len;
-#pragma unroll
-        for (int r = 0; r < EFR; ++r) {
-          uint32_t e = r * 32 + lane;
-          if (e < n_w) old[e] = L.id[r] & ~kExpanded;
-        }
+        L.for_each_prefix((int)n_w, lane, [&](int e, uint32_t nid, float) { old[e] = nid; });
         __syncwarp();
         ok = reprune_select<EFR, Dist>(g, dist, q, (uint32_t)lc, (int)a.m, old, n_w, L, vis, cnt, lane);  // dist holds q
         if (!ok) break;
       }
       const uint32_t n_sel = min((uint32_t)L.len, a.m);
-#pragma unroll
-      for (int r = 0; r < EFR; ++r) {
-        uint32_t e = r * 32 + lane;
-        if (e < n_sel) sel[e] = L.id[r] & ~kExpanded;
-      }
+      L.for_each_prefix((int)n_sel, lane, [&](int e, uint32_t nid, float) { sel[e] = nid; });
       __syncwarp();
       // connect_neighbors (core.rs:759-774): q's list is R nearest-first; q goes to the tail of each r
       {
@@ -501,6 +488,7 @@ __global__ void __launch_bounds__(32) delete_exact_kernel(Graph g, ExactArgs a) 
 
   Dist dist;
   CandList<EFR> L;
+  L.bind(a.list_mem, a.list_cap);
   Counters cnt = {0, 0, 0};
   uint32_t n_touched = 0, n_reprunes = 0;
   auto touch = [&](uint32_t id) {
@@ -658,11 +646,7 @@ __global__ void __launch_bounds__(256) build_search_kernel(Graph g, FastArgs a) 
       if (!link) continue;
       const uint32_t n_sel = min((uint32_t)L.len, a.m);
       uint32_t* out = a.sel_ids + (size_t)(tb + lc) * a.m;
-#pragma unroll
-      for (int r = 0; r < EFR; ++r) {
-        uint32_t e = r * 32 + lane;
-        if (e < n_sel) out[e] = L.id[r] & ~kExpanded;
-      }
+      L.for_each_prefix((int)n_sel, lane, [&](int e, uint32_t nid, float) { out[e] = nid; });
       if (lane == 0) a.sel_cnt[tb + lc] = n_sel;
     }
     if (!ok) {
@@ -788,11 +772,7 @@ __global__ void __launch_bounds__(256) build_reprune_kernel(Graph g, FastArgs a)
     }
     ++n_done;
     for (uint32_t i = lane; i < n_old; i += 32) a.wl_old[(size_t)w * a.lcap + i] = old[i];
-#pragma unroll
-    for (int r = 0; r < EFR; ++r) {
-      int p = r * 32 + lane;
-      if (p < L.len) a.wl_new[(size_t)w * g.W + p] = L.id[r] & ~kExpanded;
-    }
+    L.for_each_prefix(L.len, lane, [&](int p, uint32_t nid, float) { a.wl_new[(size_t)w * g.W + p] = nid; });
     if (lane == 0) a.wl_len[2 * w] = n_old, a.wl_len[2 * w + 1] = (uint32_t)L.len;
   }
   if (lane == 0) {

@@ -66,6 +66,7 @@ static int build_efr(const Index& ix) {
 // memory size / visited slots) when it applies.
 bool Index::exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) const {
   if (kind_needs_smem_query(kind) || opt_build_impl == 1) return false;
+  if (build_efr(*this) == kEfrMem) return false;  // lists beyond the register classes: register-staged kernels only
   const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
   const uint32_t slots = 8192;
   // 32-d / 128-d rows: a second stage for the one-hop lookahead of the insert's searches (search_la.cuh)
@@ -79,7 +80,7 @@ bool Index::exact_staged(size_t* smem, size_t list_bytes, uint32_t* vis_slots) c
 int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
   if (count == 0) return HNSW_OK;
   const int efr = build_efr(*this);
-  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 65536)");
   if (!exact_vis_slots) exact_vis_slots = next_pow2(std::max<uint64_t>(1u << 16, (uint64_t)ef_construction * 256));
   const uint32_t lcap = list_capacity(g.W);
   const uint32_t touched_cap = want_touched ? 1u << 16 : 0;
@@ -90,6 +91,11 @@ int Index::add_exact(uint32_t first, uint32_t count, bool want_touched) {
   cudaError_t e = cudaMemsetAsync(ctl, 0, (size_t)kCtlWords * 4, stream);
   if (e != cudaSuccess) return cuda_fail(e, "exact ctl memset");
   ExactArgs a{};
+  if (efr == kEfrMem) {
+    a.list_cap = (std::max(ef_construction, m_max_0) + 31) & ~31u;
+    if ((rc = ensure_scratch(s_list, (size_t)2 * a.list_cap * 4))) return rc;
+    a.list_mem = (uint32_t*)s_list.p;
+  }
   a.first = first;
   a.count = count;
   a.m = m;
@@ -439,7 +445,7 @@ static cudaError_t run_spec(int kind, int efr, bool small, const LaunchCfg& c, c
 int Index::add_spec(uint32_t first, uint32_t count) {
   if (count == 0) return HNSW_OK;
   const int efr = build_efr(*this);
-  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 65536)");
   const uint32_t lcap = list_capacity(g.W);
   const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
   const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
@@ -597,7 +603,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
 int Index::delete_node(uint32_t id) {
   if (id >= n_ids || h_level[id] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", id);  // core.rs:421
   const int efr = efr_for(m_max_0);  // delete only re-selects lists of at most m_max_0 entries
-  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
+  if (!efr) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 65536)");
   int rc = pull_meta();  // the device owns pool_used
   if (rc) return rc;
   const uint32_t lcap = list_capacity(g.W);
@@ -611,6 +617,11 @@ int Index::delete_node(uint32_t id) {
   cudaError_t e = cudaMemsetAsync(ctl, 0, (size_t)kCtlWords * 4, stream);
   if (e != cudaSuccess) return cuda_fail(e, "delete ctl memset");
   ExactArgs a{};
+  if (efr == kEfrMem) {
+    a.list_cap = (m_max_0 + 31) & ~31u;
+    if ((rc = ensure_scratch(s_list, (size_t)2 * a.list_cap * 4))) return rc;
+    a.list_mem = (uint32_t*)s_list.p;
+  }
   a.first = id;
   a.count = 1;
   a.m = m;
@@ -686,7 +697,7 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
   if (!data) return fail(HNSW_ERR_INVALID, "null data");
   if (mode != HNSW_BUILD_EXACT && mode != HNSW_BUILD_FAST && mode != HNSW_BUILD_SPEC) return fail(HNSW_ERR_INVALID, "unknown build mode %d", mode);
   if (n_ids + count >= 0x7FFFFFFFull) return fail(HNSW_ERR_INVALID, "too many nodes");
-  if (!build_efr(*this)) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 1024)");
+  if (!build_efr(*this)) return fail(HNSW_ERR_INVALID, "m too large for the builder (2m <= 65536)");
   int rc = pull_meta();  // the device owns pool_used
   if (rc) return rc;
   const uint32_t first = (uint32_t)n_ids;
@@ -730,7 +741,7 @@ int Index::add_batch(uint64_t count, const float* data, const int32_t* levels, i
   const uint64_t live_before = node_count;
   // ef_construction < m: select_neighbors at core.rs:531 is a genuine 2-hop sweep (build.cuh header), which only the
   // EXACT kernels compute; the batched builder would link ef_construction instead of m neighbours per node
-  if (mode == HNSW_BUILD_EXACT || ef_construction < m) {
+  if (mode == HNSW_BUILD_EXACT || ef_construction < m || build_efr(*this) == kEfrMem) {
     // overflow rows: the stream can allocate one per append in the worst case, but rows over W ids are rare (1-3 % of the
     // nodes): reserve for a bounded burst and let long streams run in pieces
     for (uint32_t pos = 0; pos < rest && !rc; pos += 65536) {

@@ -229,7 +229,7 @@ int Index::pull_meta() {
 Index::~Index() {
   if (cudaSetDevice(device) != cudaSuccess) return;
   void* ptrs[] = {g.vecs, g.adj0, g.ovf0, g.upper_base, g.level, g.adjU, g.ovfU, g.pool, g.meta, g.locks,
-                  d_stamp0, d_stampU, d_ver0, d_verU, s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p, s_bvis.p, s_spec.p};
+                  d_stamp0, d_stampU, d_ver0, d_verU, s_in.p, s_out.p, s_vis.p, s_ctl.p, s_build.p, s_stage.p, s_bvis.p, s_spec.p, s_list.p};
   if (h_retry_seen) cudaFreeHost(h_retry_seen);
   if (h_stage) cudaFreeHost(h_stage);
   for (void* p : ptrs)
@@ -447,7 +447,7 @@ int hnsw_index_create(uint32_t data_dim, uint32_t m, uint32_t ef_construction, i
   if (!out) return fail(HNSW_ERR_INVALID, "null out pointer");
   *out = nullptr;
   if (data_dim == 0 || m == 0 || ef_construction == 0) return fail(HNSW_ERR_INVALID, "dim, m and ef_construction must be > 0");
-  if (efr_for(ef_construction) == 0) return fail(HNSW_ERR_INVALID, "ef_construction > 1024 is not supported");
+  if (efr_for(ef_construction) == 0) return fail(HNSW_ERR_INVALID, "ef_construction > %u is not supported", kMaxMemEf);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(HNSW_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));

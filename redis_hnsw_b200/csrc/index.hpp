@@ -79,7 +79,7 @@ struct Index {
   uint32_t opt_spec_mult = 0;     // SPEC: adaptive window = mult / 10 x (inserts committed per round, running mean); 0 = 40
 
   // scratch
-  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis, s_spec;
+  Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis, s_spec, s_list;
 
   ~Index();
   int use_device();

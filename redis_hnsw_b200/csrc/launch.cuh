@@ -16,7 +16,11 @@ struct LaunchCfg {
   cudaStream_t stream;
 };
 
-// list registers per lane for a given ef (0 = unsupported)
+// the memory-backed list class: ef / ef_construction / 2m up to kMaxMemEf entries, register-staged kernels only
+constexpr int kEfrMem = 64;
+constexpr uint32_t kMaxMemEf = 65536;
+
+// list registers per lane for a given ef (0 = unsupported, kEfrMem = memory-backed list)
 inline int efr_for(uint32_t ef) {
   if (ef == 0) return 0;
   if (ef <= 32) return 1;
@@ -24,7 +28,8 @@ inline int efr_for(uint32_t ef) {
   if (ef <= 128) return 4;
   if (ef <= 256) return 8;
   if (ef <= 512) return 16;
-  if (ef <= 1024) return 32;  // DRAFT (branch): 64 list registers per lane
+  if (ef <= 1024) return 32;
+  if (ef <= kMaxMemEf) return kEfrMem;  // beyond the register classes: the list lives in memory (CandList<0>, search.cuh)
   return 0;
 }
 
@@ -98,13 +103,17 @@ cudaError_t run_kernel(int id, const LaunchCfg& c, const KernelArgs& ka, bool oc
     case kKernSearchSmem: HNSW_RUN((search_knn_kernel<EFR, Dist, true>), SearchArgs)
     case kKernSearchGlobal: HNSW_RUN((search_knn_kernel<EFR, Dist, false>), SearchArgs)
     case kKernLevel: HNSW_RUN((search_level_kernel<EFR, Dist>), LevelArgs)
-    case kKernBuildSearchSmem: HNSW_RUN((build_search_kernel<EFR, Dist, true>), FastArgs)
-    case kKernBuildSearchGlobal: HNSW_RUN((build_search_kernel<EFR, Dist, false>), FastArgs)
-    case kKernBuildReprune: HNSW_RUN((build_reprune_kernel<EFR, Dist>), FastArgs)
     case kKernExact: HNSW_RUN((insert_exact_kernel<EFR, Dist>), ExactArgs)
     case kKernDelete: HNSW_RUN((delete_exact_kernel<EFR, Dist>), ExactArgs)
   }
-  if constexpr (Dist::kStaged) {
+  if constexpr (EFR > 0) {  // the batched builder has no memory-backed class: such requests run the EXACT stream
+    switch (id) {
+      case kKernBuildSearchSmem: HNSW_RUN((build_search_kernel<EFR, Dist, true>), FastArgs)
+      case kKernBuildSearchGlobal: HNSW_RUN((build_search_kernel<EFR, Dist, false>), FastArgs)
+      case kKernBuildReprune: HNSW_RUN((build_reprune_kernel<EFR, Dist>), FastArgs)
+    }
+  }
+  if constexpr (Dist::kStaged && EFR > 0) {
     switch (id) {
       case kKernSearch2 + 0: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, uint32_t>), SearchArgs)
       case kKernSearch2 + 1: HNSW_RUN((search_knn2_kernel<EFR, Dist::C, 4, uint16_t>), SearchArgs)
@@ -162,6 +171,7 @@ cudaError_t run_kind(int id, int efr, const LaunchCfg& c, const KernelArgs& ka, 
   }
   if constexpr (PART == 0 || PART == 3) {
     if (efr == 32) return run_kernel<32, Dist>(id, c, ka, occupancy_only, occ);
+    if (efr == kEfrMem) return run_kernel<0, Dist>(id, c, ka, occupancy_only, occ);
   }
   return cudaErrorInvalidValue;
 }

@@ -247,6 +247,32 @@ struct CandList {
     }
   }
 
+  __device__ __forceinline__ void bind(uint32_t*, uint32_t) {}  // registers: nothing to bind (see CandList<0>)
+  // f(e, id, sim) for the entries e < n this lane owns (e % 32 == lane)
+  template <class F>
+  __device__ __forceinline__ void for_each_prefix(int n, int lane, F f) const {
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) {
+      const int e = r * 32 + lane;
+      if (e < n) f(e, id[r] & ~kExpanded, sim[r]);
+    }
+  }
+  __device__ __forceinline__ bool contains(uint32_t x, int) const {
+    bool hit = false;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r) hit |= (id[r] & ~kExpanded) == x;   // an empty slot masks to 0x7FFFFFFF, not a node id
+    return __any_sync(kFull, hit);
+  }
+
+  // id of entry `pos` (warp-uniform), on every lane
+  __device__ __forceinline__ uint32_t entry_at(int pos, int) const {
+    uint32_t x = kEmpty;
+#pragma unroll
+    for (int r = 0; r < EFR; ++r)
+      if (r == (pos >> 5)) x = id[r];
+    return __shfl_sync(kFull, x, pos & 31) & ~kExpanded;
+  }
+
   // read entry `pos` (warp-uniform) and optionally mark it expanded
   __device__ __forceinline__ void get(int pos, int lane, bool mark, uint32_t& nid, float& s) {
     uint32_t vi = kEmpty;
@@ -261,6 +287,87 @@ struct CandList {
     nid = __shfl_sync(kFull, vi, l) & ~kExpanded;
     s = __shfl_sync(kFull, vs, l);
   }
+};
+
+// ---------------------------------------------------------------- candidate list in memory (ef beyond the register classes)
+
+// CandList<0>: the same sorted list, kept in the warp's slice of a global-memory scratch buffer instead of registers.
+// The reference accepts any EFCON (lib.rs:53, core.rs:322-346); the register classes end at 1024 entries, and this class
+// takes over beyond that (register-staged kernels only: search_knn_kernel, search_level_kernel, the one-warp insert and
+// delete).  Every operation is O(ef / 32) warp steps — a compatibility path, not a fast one.
+template <>
+struct CandList<0> {
+  float* sim;        // [cap] descending
+  uint32_t* id;      // [cap], bit 31 = expanded
+  int len;           // warp-uniform
+  float worst;
+  int ucur;          // every entry before this position is expanded
+  static constexpr bool kWide = false;
+
+  __device__ __forceinline__ void bind(uint32_t* mem, uint32_t cap) {
+    sim = reinterpret_cast<float*>(mem);
+    id = mem + cap;
+  }
+  __device__ __forceinline__ void init() {
+    len = 0, ucur = 0;
+    worst = -CUDART_INF_F;
+  }
+  __device__ __forceinline__ bool admits(float s, int ef) const { return len < ef || s > worst; }
+
+  __device__ __forceinline__ void insert(float s, uint32_t nid, int ef, int lane) {
+    int p = 0;                                                 // entries with sim >= s (new entry goes after equal sims)
+    for (int base = 0; base < len; base += 32) {
+      const uint32_t b = __ballot_sync(kFull, base + lane < len && sim[base + lane] >= s);
+      p += __popc(b);
+      if (b != kFull) break;
+    }
+    const int newlen = len < ef ? len + 1 : ef;
+    for (int hi = newlen - 1; hi > p; hi -= 32) {              // shift [p, newlen - 1) one slot to the right, from the end
+      const int e = hi - lane;
+      const bool act = e > p;
+      float vs = 0.f;
+      uint32_t vi = kEmpty;
+      if (act) vs = sim[e - 1], vi = id[e - 1];
+      __syncwarp();
+      if (act) sim[e] = vs, id[e] = vi;
+      __syncwarp();
+    }
+    if (lane == 0 && p < newlen) sim[p] = s, id[p] = nid;
+    __syncwarp();
+    len = newlen;
+    if (len == ef) worst = sim[ef - 1];
+    if (p < ucur) ucur = p;
+  }
+  __device__ __forceinline__ int first_unexpanded() {
+    for (int base = ucur & ~31; base < len; base += 32) {
+      const int e = base + lane_id();
+      const uint32_t b = __ballot_sync(kFull, e < len && e >= ucur && !(id[e] & kExpanded));
+      if (b) {
+        ucur = base + __ffs(b) - 1;
+        return ucur;
+      }
+    }
+    ucur = len;
+    return -1;
+  }
+  __device__ __forceinline__ void get(int pos, int lane, bool mark, uint32_t& nid, float& s) {
+    nid = id[pos] & ~kExpanded;
+    s = sim[pos];
+    __syncwarp();
+    if (mark && lane == 0) id[pos] |= kExpanded;
+    __syncwarp();
+  }
+  // f(e, id, sim) for the entries e < n this lane owns (e % 32 == lane)
+  template <class F>
+  __device__ __forceinline__ void for_each_prefix(int n, int lane, F f) const {
+    for (int e = lane; e < n; e += 32) f(e, id[e] & ~kExpanded, sim[e]);
+  }
+  __device__ __forceinline__ bool contains(uint32_t x, int lane) const {
+    bool hit = false;
+    for (int e = lane; e < len; e += 32) hit |= (id[e] & ~kExpanded) == x;
+    return __any_sync(kFull, hit);
+  }
+  __device__ __forceinline__ uint32_t entry_at(int pos, int) const { return id[pos] & ~kExpanded; }
 };
 
 // ---------------------------------------------------------------- exact visited set (open addressing)
@@ -531,6 +638,8 @@ struct SearchArgs {
   uint32_t vis_slots;     // per-warp visited slots (power of two)
   uint32_t* vis_global;   // [warps][vis_slots] when the table lives in global memory
   int retry_pass;         // 1: take query indices from retry_list
+  uint32_t* list_mem;     // CandList<0> only: [warps of the grid][2 * list_cap] words
+  uint32_t list_cap;
 };
 
 template <int EFR, class Dist, bool VIS_SMEM>
@@ -556,6 +665,8 @@ __global__ void __launch_bounds__(256) search_knn_kernel(Graph g, SearchArgs a) 
   const uint32_t total = a.retry_pass ? *a.retry_count : a.nq;
   Dist dist;
   CandList<EFR> L;
+  L.bind(a.list_mem + ((size_t)blockIdx.x * warps + warp) * 2 * a.list_cap, a.list_cap);
+  constexpr uint32_t kRegCap = EFR * 32;                       // 0 for the memory-backed class
 
   for (;;) {
     uint32_t wi = 0;
@@ -584,19 +695,16 @@ __global__ void __launch_bounds__(256) search_knn_kernel(Graph g, SearchArgs a) 
       continue;
     }
     // results nearest-first (core.rs:878-891); unused slots are padded
-#pragma unroll
-    for (int r = 0; r < EFR; ++r) {
-      uint32_t e = r * 32 + lane;
-      if (e < a.k) {
-        bool have = ok && e < n_out;
-        a.ids[(size_t)qi * a.k + e] = have ? (L.id[r] & ~kExpanded) : kEmpty;
-        a.sims[(size_t)qi * a.k + e] = have ? L.sim[r] : -CUDART_INF_F;
-      }
-    }
-    for (uint32_t e = EFR * 32 + lane; e < a.k; e += 32) {     // k beyond the list capacity
+    if (!ok) n_out = 0;
+    L.for_each_prefix((int)n_out, lane, [&](int e, uint32_t nid, float sv) {
+      a.ids[(size_t)qi * a.k + e] = nid;
+      a.sims[(size_t)qi * a.k + e] = sv;
+    });
+    for (uint32_t e = n_out + lane; e < a.k; e += 32) {        // unused slots are padded
       a.ids[(size_t)qi * a.k + e] = kEmpty;
       a.sims[(size_t)qi * a.k + e] = -CUDART_INF_F;
     }
+    (void)kRegCap;
     if (lane == 0) {
       a.counts[qi] = n_out;
       if (a.stats) {
@@ -620,6 +728,8 @@ struct LevelArgs {
   uint32_t* n_out;  // [1]; 0xFFFFFFFF on visited overflow
   uint32_t vis_slots;
   uint32_t* vis_global;
+  uint32_t* list_mem;  // CandList<0> only: [2 * list_cap] words
+  uint32_t list_cap;
 };
 
 template <int EFR, class Dist>
@@ -634,20 +744,17 @@ __global__ void __launch_bounds__(32) search_level_kernel(Graph g, LevelArgs a) 
   Dist dist;
   dist.load_query(a.query, reinterpret_cast<float*>(smem), g.dim, lane);
   CandList<EFR> L;
+  L.bind(a.list_mem, a.list_cap);
   Counters cnt = {0, 0, 0};
   bool ok = search_layer<EFR, Dist>(g, dist, a.entry, (int)a.ef, a.level, L, vis, cnt, lane);
   if (!ok) {
     if (lane == 0) *a.n_out = 0xFFFFFFFFu;
     return;
   }
-#pragma unroll
-  for (int r = 0; r < EFR; ++r) {
-    int e = r * 32 + lane;
-    if (e < L.len) {
-      a.ids[e] = L.id[r] & ~kExpanded;
-      a.sims[e] = L.sim[r];
-    }
-  }
+  L.for_each_prefix(L.len, lane, [&](int e, uint32_t nid, float sv) {
+    a.ids[e] = nid;
+    a.sims[e] = sv;
+  });
   if (lane == 0) *a.n_out = (uint32_t)L.len;
 }
 

@@ -65,9 +65,10 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   if (k == 0) return fail(HNSW_ERR_INVALID, "k must be > 0");
   if (ef == 0) ef = ef_construction;  // core.rs:485
   const int efr = efr_for(ef);
-  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..1024)", ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..%u)", ef, kMaxMemEf);
   const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
-  last_search_staged = staged_kind && opt_search_impl != 1 && (opt_search_impl == 2 || !d_stats);
+  // ef beyond the register classes: the memory-backed list exists in the register-staged kernel family only
+  last_search_staged = efr != kEfrMem && staged_kind && opt_search_impl != 1 && (opt_search_impl == 2 || !d_stats);
   if (last_search_staged) return search_device2(nq, d_q, k, ef, efr, d_ids, d_sims, d_counts, d_stats, s);
   if (!h_retry_seen) {
     cudaError_t e = cudaHostAlloc((void**)&h_retry_seen, 16, cudaHostAllocDefault);
@@ -87,7 +88,9 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   int occ = occupancy(kind, vis_smem ? kKernSearchSmem : kKernSearchGlobal, efr, block, smem);
   if (occ < 1) return fail(HNSW_ERR_CUDA, "search kernel cannot be resident (block %d, smem %zu)", block, smem);
   if (opt_ctas_per_sm > 0) occ = std::min(occ, opt_ctas_per_sm);
+  if (efr == kEfrMem) occ = 1;  // every warp carries 8 * ef bytes of list and a large visited table in global memory
   int grid = (int)std::min<uint64_t>((uint64_t)num_sms * occ, (nq + warps - 1) / warps);
+  const uint32_t list_cap = efr == kEfrMem ? ((ef + 31) & ~31u) : 0;
 
   // retry pass: global-memory tables, 4x the slots (at least 16K), one CTA of 4 warps per SM
   const uint32_t big_slots = next_pow2(std::max<uint64_t>(16384, (uint64_t)slots * 4));
@@ -98,11 +101,14 @@ int Index::search_device(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef,
   int rc = ensure_scratch(s_vis, vis1_bytes + vis2_bytes);
   if (rc) return rc;
   if ((rc = ensure_scratch(s_ctl, 64 + (size_t)nq * 4))) return rc;
+  if (list_cap && (rc = ensure_scratch(s_list, (size_t)std::max(grid * warps, grid2 * warps2) * 2 * list_cap * 4))) return rc;
   uint32_t* ctl = (uint32_t*)s_ctl.p;
   cudaError_t e = cudaMemsetAsync(ctl, 0, 64, s);
   if (e != cudaSuccess) return cuda_fail(e, "search ctl memset");
 
   SearchArgs a{};
+  a.list_mem = (uint32_t*)s_list.p;
+  a.list_cap = list_cap;
   a.queries = d_q;
   a.nq = (uint32_t)nq;
   a.k = k;
@@ -291,7 +297,7 @@ int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uin
     const uint32_t ef_eff = ef ? ef : ef_construction;
     const int efr = efr_for(ef_eff);
     const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
-    if (!stats && nq >= 8192 && efr && staged_kind && opt_search_impl != 1 && nq <= 0x7FFFFFFFull) {
+    if (!stats && nq >= 8192 && efr && efr != kEfrMem && staged_kind && opt_search_impl != 1 && nq <= 0x7FFFFFFFull) {
       return search_host_pipelined(nq, q, k, ef_eff, efr, ids, sims, counts, (const float*)s_in.p, d_ids, d_sims, d_counts);
     }
   }
@@ -343,7 +349,7 @@ int Index::search_host(uint64_t nq, const float* q, uint32_t k, uint32_t ef, uin
 int Index::search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t level, uint32_t* ids, float* sims,
                              uint32_t* n_out) {
   const int efr = efr_for(ef);
-  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..1024)", ef);
+  if (!efr) return fail(HNSW_ERR_INVALID, "ef = %u is not supported (1..%u)", ef, kMaxMemEf);
   if (ep >= n_ids || h_level[ep] < 0) return fail(HNSW_ERR_NOT_FOUND, "Node: %u does not exist", ep);
   const uint32_t slots = next_pow2(std::max<uint64_t>(65536, (uint64_t)ef * 512));
   int rc = ensure_scratch(s_vis, (size_t)slots * 4);
@@ -352,7 +358,11 @@ int Index::search_level_host(const float* q, uint32_t ep, uint32_t ef, uint32_t 
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   if ((rc = ensure_scratch(s_out, al((size_t)ef * 4) * 2 + 256))) return rc;
   char* o = (char*)s_out.p;
+  const uint32_t list_cap = efr == kEfrMem ? ((ef + 31) & ~31u) : 0;
+  if (list_cap && (rc = ensure_scratch(s_list, (size_t)2 * list_cap * 4))) return rc;
   LevelArgs a{};
+  a.list_mem = (uint32_t*)s_list.p;
+  a.list_cap = list_cap;
   a.query = (const float*)s_in.p;
   a.entry = ep;
   a.ef = ef;

@@ -11,6 +11,7 @@ CASES = {
     "cfg1_10k_d32_m5": (10000, 32, 5, 100, "uniform", 2000),      # BASELINE configs[0]
     "d128_m16": (6000, 128, 16, 200, "lowrank16", 1500),          # configs[1] parameters, small N
     "d768_m32": (1200, 768, 32, 120, "lowrank32", 300),           # configs[2] shape, small N / efCon
+    "cfg3_5k_d768_m32_efc400": (5000, 768, 32, 400, "lowrank32", 300),   # configs[2] parameters in full (M=32, efCon=400)
     "d96_m8_generic": (3000, 96, 8, 64, "uniform", 500),          # dim % 32 == 0 without a specialised kernel
     "d20_m6_scalar": (2000, 20, 6, 48, "uniform", 500),           # dim % 32 != 0 -> reference scalar path
     "d64_m6_generic_v2": (2000, 64, 6, 48, "uniform", 400),       # generic kind, 2-wide row loads (dim/32 % 4 == 2)

@@ -163,7 +163,7 @@ def test_null_handle_and_bad_arguments_fail_cleanly(built):
         assert b"null index handle" in L.hnsw_last_error(), name
     L.hnsw_index_destroy(null)              # a no-op, like free(NULL)
     out = C.c_void_p(0)
-    for dim, m, efc in ((0, 16, 200), (128, 0, 200), (128, 16, 0), (128, 16, 1025)):
+    for dim, m, efc in ((0, 16, 200), (128, 0, 200), (128, 16, 0), (128, 16, 65537)):
         assert L.hnsw_index_create(dim, m, efc, -1, C.byref(out)) == _lib.ERR_INVALID
         assert not out.value
     assert L.hnsw_index_create(128, 16, 200, -1, None) == _lib.ERR_INVALID

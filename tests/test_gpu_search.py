@@ -140,6 +140,44 @@ def test_ef_up_to_1024():
     assert np.array_equal(go["row_offs"], gd["row_offs"]) and np.array_equal(go["nbrs"], gd["nbrs"])
 
 
+def test_ef_beyond_the_register_classes():
+    """The reference accepts any EFCON (lib.rs:53, core.rs:322-346) and searches with it (core.rs:485).  Beyond the largest
+    register class (1024 entries) the candidate list lives in memory (CandList<0>): search parity at ef 1500 / 3000, an
+    exact build with ef_construction = 1500 identical to the oracle's, NODE.ADD / NODE.DEL on it, and a clean error past
+    the supported maximum."""
+    import oracle
+    import redis_hnsw_b200 as r
+
+    c = case("d128_m16")
+    dev = device_index("d128_m16")
+    for ef in (1500, 3000):
+        assert_search_parity(dev, c["oracle"], c["q"][:300], 10, ef, min_tie_free=0.02)
+        ids, sims = dev.search_level(c["q"][0], c["graph"]["entry"], ef, 0)
+        oids, osims = c["oracle"].search_level(c["q"][0], c["graph"]["entry"], ef, 0)
+        assert len(ids) == len(oids) and np.array_equal(np.sort(ids), np.sort(oids))
+    n = 1300
+    orc = oracle.Oracle(c["dim"], c["m"], 1500)
+    orc.add_batch(c["x"][:n], c["levels"][:n])
+    for mode in (r.BUILD_EXACT, r.BUILD_SPEC, r.BUILD_FAST):      # SPEC and FAST hand such an index to the EXACT stream
+        d2 = r.DeviceIndex(c["dim"], c["m"], 1500)
+        d2.add_batch(c["x"][:n], c["levels"][:n], mode=mode)
+        go, gd = orc.export_graph(), d2.export_graph()
+        assert np.array_equal(go["row_offs"], gd["row_offs"]) and np.array_equal(go["nbrs"], gd["nbrs"])
+    for i in range(n, n + 10):
+        assert d2.add(c["x"][i], int(c["levels"][i])) == orc.add(c["x"][i], int(c["levels"][i]))
+    d2.delete(77)
+    orc.delete(77)
+    go, gd = orc.export_graph(), d2.export_graph()
+    assert np.array_equal(go["row_offs"], gd["row_offs"]) and np.array_equal(go["nbrs"], gd["nbrs"])
+    ids, sims, counts = d2.search_batch(c["q"][:50], 10)         # ef = 0 -> ef_construction = 1500 (core.rs:485)
+    oids, osims, ocounts, ost, _ = orc.search_batch(c["q"][:50], 10)
+    ok = ost[:, 3] == 0
+    assert np.array_equal(counts, ocounts) and np.array_equal(ids[ok], oids[ok])
+    r.DeviceIndex(32, 5, 65536).close()
+    with pytest.raises(r.HNSWError, match="not supported"):
+        r.DeviceIndex(32, 5, 65537)
+
+
 def test_default_ef_is_ef_construction():
     """core.rs:485: search_knn always searches with ef = ef_construction."""
     c = case("cfg1_10k_d32_m5")
@@ -271,6 +309,6 @@ def test_errors_and_empty_index():
     ids, sims, counts = dev.search_batch(np.zeros((4, 32), np.float32), 5)
     assert np.all(counts == 0) and np.all(ids == 0xFFFFFFFF)
     with pytest.raises(r.HNSWError, match="not supported"):
-        dev.search_batch(np.zeros((4, 32), np.float32), 5, ef=5000)
+        dev.search_batch(np.zeros((4, 32), np.float32), 5, ef=70000)
     with pytest.raises(r.HNSWError):
         r.DeviceIndex(0, 5, 100)

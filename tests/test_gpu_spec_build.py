@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
     ("cfg1_10k_d32_m5", 10000),   # BASELINE configs[0], every node
     ("d128_m16", 6000),           # configs[1] parameters
     ("d768_m32", 1200),           # configs[2] shape (bulk-async row copies)
+    ("cfg3_5k_d768_m32_efc400", 5000),   # configs[2] parameters in full: M=32, efCon=400 (16 list registers per lane)
     ("d96_m8_generic", 1500),     # no staged kernel for this dimension: SPEC hands the stream to the one-warp EXACT kernel
 ])
 def test_spec_build_equals_oracle_graph(name, n):
@@ -47,6 +48,9 @@ def test_spec_build_equals_oracle_graph(name, n):
         assert st["spec_rounds"] > 0 and st["spec_executions"] >= n - 1
         assert st["spec_rounds"] < n - 1, "no round ever committed more than one insert: speculation is not working"
     assert_search_parity(dev, orc, c["q"][:200], 10, 64)
+    if name.startswith("cfg3"):                                   # the literal efSearch of configs[2] and ef = efCon
+        assert_search_parity(dev, orc, c["q"][:200], 10, 128)
+        assert_search_parity(dev, orc, c["q"][:100], 10, 400, min_tie_free=0.5)
 
 
 def test_spec_graph_does_not_depend_on_the_window():
