@@ -500,7 +500,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   while (f < end) {
     const double t_round = trace ? now_ms() : 0;
-    uint32_t B = opt_spec_window ? opt_spec_window : (uint32_t)std::max(8.0, 0.1 * (opt_spec_mult ? opt_spec_mult : 40) * ema);
+    uint32_t B = opt_spec_window ? opt_spec_window : (uint32_t)std::max(8.0, 0.1 * (opt_spec_mult ? opt_spec_mult : 30) * ema);
     B = std::min(std::min(B, resident), end - f);
     // a node that raises max_layer becomes the enterpoint of everything after it (core.rs:587-593): the window ends there
     uint32_t wend = f + B;

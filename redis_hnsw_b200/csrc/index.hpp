@@ -59,7 +59,7 @@ struct Index {
   int opt_row_copy = 1;           // staged search: 1 = cp.async row copies where a row is <= 2 instructions (32-d, 128-d), 0 = bulk-async copies everywhere (search2.cuh, COPY)
   int opt_recent_ways = 1;        // DRAFT: 2 = two-way set-associative visited tags (Recent<Way2>), cp.async kinds only
   int opt_lookahead = 0;          // 1 = calls whose warps are all resident use search_knn2_la_kernel (one-hop lookahead, search_la.cuh; measured: no gain)
-  int opt_search_cta = 0;         // DRAFT: 1 = calls with few queries run one query per CTA of 4 warps (search_knn2_cta_kernel)
+  int opt_search_cta = 1;         // 1 = calls with at most 2 queries per SM run one query per CTA of 4 warps (search_knn2_cta_kernel: -10 % latency)
   int opt_recent_tag = 0;         // 0 auto (16-bit tags when every id fits), 32 = force 32-bit entries
   uint32_t opt_recent_slots = 0;  // direct-mapped visited slots of the TMA-staged kernel, 0 = auto
   uint32_t opt_build_batch = 0;
@@ -76,7 +76,7 @@ struct Index {
   uint32_t* d_ver0 = nullptr;     // [cap_nodes] SPEC builder row stamps: 1 + id of the last insert that wrote the row
   uint32_t* d_verU = nullptr;     // [cap_upper]
   uint32_t opt_spec_window = 0;   // SPEC: fixed window size (0 = adaptive)
-  uint32_t opt_spec_mult = 0;     // SPEC: adaptive window = mult / 10 x (inserts committed per round, running mean); 0 = 40
+  uint32_t opt_spec_mult = 0;     // SPEC: adaptive window = mult / 10 x (inserts committed per round, running mean); 0 = 30 (3.0x: best of 1.5x .. 8x at 1M nodes, profiles/r2_spec_build.md)
 
   // scratch
   Scratch s_in, s_out, s_vis, s_ctl, s_build, s_stage, s_bvis, s_spec, s_list;

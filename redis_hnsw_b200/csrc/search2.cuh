@@ -265,7 +265,12 @@ __device__ __forceinline__ float staged_partial(const float (&q)[C], const float
 // publishes the compacted ids, and all four warps copy, multiply and reduce 8 rows each, so the ~450 dependent
 // instructions a 32-row round costs one warp (copies 147, partials 200, reduction 96; profiles/r1e_search.md) shrink
 // to ~120 on the critical path.  Two named barriers per round.  NOT YET RUN ON HARDWARE.
-__device__ __forceinline__ void cta_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// every warp arrives converged (compute-sanitizer synccheck flags a warp that reaches bar.sync in pieces, e.g. right after
+// an `if (lane == 0)` store: found by the r2 sanitizer run, harmless on sm_100 but not something to rely on)
+__device__ __forceinline__ void cta_bar(int id) {
+  __syncwarp();
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
 
 template <int C, int S, class T>
 __device__ __forceinline__ void cta_round(const Graph& g, Warp2<C, S, T>& w, int nr, int wi, int lane) {

@@ -176,7 +176,9 @@ int Index::search_device2(uint64_t nq, const float* d_q, uint32_t k, uint32_t ef
   while ((1u << slot_bits) < slots) ++slot_bits;
   // 16-bit tags identify an id exactly only below 2^(log2(slots) + 15)
   const bool tag16 = opt_recent_tag != 32 && slot_bits + 15 < 32 && n_ids <= (1ull << (slot_bits + 15));
-  if (opt_search_cta && nq <= 4ull * (uint64_t)num_sms) {  // DRAFT: one query per CTA of 4 warps (search2.cuh, COPY == 2)
+  // few queries (one HNSW.SEARCH, a handful per SM): one query per CTA of 4 warps that share the row copies, partial sums
+  // and reduction of every hop (search2.cuh, COPY == 2): 211 -> 185 us for one query, 349 -> 303 us for 148 (profiles/r2_experiments.md)
+  if (opt_search_cta && !d_stats && (kind == kKindR4 || kind == kKindR1) && nq <= 2ull * (uint64_t)num_sms) {
     const size_t smem_cta = warp2_smem_bytes(dim, 32, slots, tag16 ? 2 : 4) + 256;
     if (smem_cta <= max_smem) {
       int rc0 = ensure_scratch(s_ctl, std::max<size_t>(64 + (size_t)nq * 4, 64 * kCtlSlots));

@@ -80,8 +80,8 @@ def test_latency_mode_parity(name, efs):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("name,efs", [("cfg1_10k_d32_m5", (1, 16, 100)), ("d128_m16", (8, 64, 200, 512)), ("d768_m32", (16, 128))])
 def test_cta_latency_kernel_parity(name, efs):
-    """DRAFT (branch r2-cta-draft): option search_cta = 1 runs one query per CTA of 4 warps for small calls
-    (search_knn2_cta_kernel).  First thing to run on hardware next round — under a timeout: two named barriers per round."""
+    """Calls with at most two queries per SM run one query per CTA of 4 warps (search_knn2_cta_kernel, option search_cta,
+    default on for 32-d / 128-d rows): same ids, sims and counts as the oracle; also with the option off."""
     c = case(name)
     dev = device_index(name)
     dev.set_option("search_cta", 1)
@@ -95,11 +95,18 @@ def test_cta_latency_kernel_parity(name, efs):
             assert np.array_equal(ids[ok], oids[ok])
             assert np.array_equal(sims[ok].view(np.uint32), osims[ok].view(np.uint32))
     dev.set_option("search_cta", 0)
+    q = c["q"][:40]
+    oids, osims, ocounts, ost, _ = c["oracle"].search_batch(q, 10, ef=efs[-1])
+    ok = ost[:, 3] == 0
+    ids, sims, counts = dev.search_batch(q, 10, ef=efs[-1])
+    assert np.array_equal(counts, ocounts) and np.array_equal(ids[ok], oids[ok])
+    dev.set_option("search_cta", 1)
 
 
 @pytest.mark.parametrize("name", ["cfg1_10k_d32_m5", "d128_m16"])
 def test_two_way_visited_sets_parity(name):
-    """DRAFT (branch r2-cta-draft): option recent_ways = 2 (Recent<Way2>): same results, fewer or equal re-evaluations."""
+    """Option recent_ways = 2 (Recent<Way2>): same results, fewer or equal re-evaluations (not the default: it costs more
+    than it saves, profiles/r2_experiments.md)."""
     c = case(name)
     dev = device_index(name)
     q = c["q"][:300]
@@ -120,8 +127,8 @@ def test_two_way_visited_sets_parity(name):
 
 
 def test_ef_up_to_1024():
-    """DRAFT (branch r2-cta-draft): a sixth list class (32 registers per lane x 2) lifts the ef / ef_construction limit
-    from 512 to 1024 — search parity at ef 600 / 1024 and an exact build with ef_construction = 700."""
+    """The sixth register class (32 list registers per lane x 2) serves ef / ef_construction up to 1024 — search parity at
+    ef 600 / 1024 and an exact build with ef_construction = 700."""
     import oracle
     import redis_hnsw_b200 as r
 
