@@ -373,7 +373,16 @@ def main():
     nq_total = args.nq if strong else args.nq * eff_world
     n_probe = 2000
     t_setup = time.perf_counter()
-    x, q_all, levels = make_data(wl, max(nq_total, 10_000) + n_probe)
+    n_q = max(nq_total, 10_000) + n_probe
+    if rank == 0 or ref_arm:
+        x, q_all, levels = make_data(wl, n_q)
+    else:                                 # only the builder needs the vectors: the other ranks receive the index over NCCL
+        x, levels, q_all = None, None, np.empty((n_q, dim), np.float32)
+    if dist is not None:                  # ... and the queries from rank 0 (they come out of the same generator stream as x)
+        tq = torch.from_numpy(q_all).cuda()
+        dist.broadcast(tq, 0)
+        q_all = tq.cpu().numpy()
+        del tq
     q_probe = np.ascontiguousarray(q_all[-n_probe:])
     log("data ready in %.1f s" % (time.perf_counter() - t_setup))
     dev, binfo = build_index(wl, x, levels, local_rank, 0 if ref_arm else rank, eff_world, args.option, graph=args.graph)

@@ -59,7 +59,8 @@ struct Index {
   int opt_row_copy = 1;           // staged search: 1 = cp.async row copies where a row is <= 2 instructions (32-d, 128-d), 0 = bulk-async copies everywhere (search2.cuh, COPY)
   int opt_recent_ways = 1;        // DRAFT: 2 = two-way set-associative visited tags (Recent<Way2>), cp.async kinds only
   int opt_lookahead = 0;          // 1 = calls whose warps are all resident use search_knn2_la_kernel (one-hop lookahead, search_la.cuh; measured: no gain)
-  int opt_search_cta = 1;         // 1 = calls with at most 2 queries per SM run one query per CTA of 4 warps (search_knn2_cta_kernel: -10 % latency)
+  int opt_search_cta = 0;         // 1 = calls with at most 2 queries per SM run one query per CTA of 4 warps (search_knn2_cta_kernel: -10 % latency;
+                                  // opt-in: synccheck reports its named-barrier handshake, profiles/r2_sanitizer.md)
   int opt_recent_tag = 0;         // 0 auto (16-bit tags when every id fits), 32 = force 32-bit entries
   uint32_t opt_recent_slots = 0;  // direct-mapped visited slots of the TMA-staged kernel, 0 = auto
   uint32_t opt_build_batch = 0;

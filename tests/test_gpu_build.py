@@ -24,15 +24,30 @@ def _lists(g):
     return out
 
 
-def _assert_same_graph(gd, go):
+def _assert_same_graph(gd, go, x=None):
+    """Device graph == oracle graph, list by list and in list order.  With the vectors `x` given, ONE kind of difference is
+    tolerated and counted: two entries of a list swapped whose sims to the list's node are bit-equal — the reference leaves
+    the order of such a pair to BinaryHeap internals (SURVEY fact #7), so no fixture may pin it."""
     assert np.array_equal(gd["levels"], go["levels"])
     assert gd["entry"] == go["entry"] and gd["max_layer"] == go["max_layer"]
-    if not (np.array_equal(gd["row_offs"], go["row_offs"]) and np.array_equal(gd["nbrs"], go["nbrs"])):
-        ld, lo = _lists(gd), _lists(go)
-        bad = [k for k in lo if not np.array_equal(ld[k], lo[k])]
+    if np.array_equal(gd["row_offs"], go["row_offs"]) and np.array_equal(gd["nbrs"], go["nbrs"]):
+        return 0
+    ld, lo = _lists(gd), _lists(go)
+    bad = [k for k in lo if not np.array_equal(ld[k], lo[k])]
+    tied = 0
+    if x is not None:
+        for (i, l) in list(bad):
+            a, b = ld[(i, l)], lo[(i, l)]
+            if a.size == b.size and np.array_equal(np.sort(a), np.sort(b)) and all(
+                    oracle.euclidean(x[i], x[int(u)]) == oracle.euclidean(x[i], x[int(v)]) for u, v in zip(a, b) if u != v):
+                bad.remove((i, l))
+                tied += 1
+    if bad:
         k = bad[0]
         raise AssertionError("%d of %d adjacency lists differ; first (node, level)=%r device=%r oracle=%r"
                              % (len(bad), len(lo), k, ld[k], lo[k]))
+    assert tied <= 3, "%d lists differ by the order of tied entries: too many to be accidents of f32" % tied
+    return tied
 
 
 @pytest.mark.parametrize("name,n", [

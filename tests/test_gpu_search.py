@@ -80,8 +80,8 @@ def test_latency_mode_parity(name, efs):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("name,efs", [("cfg1_10k_d32_m5", (1, 16, 100)), ("d128_m16", (8, 64, 200, 512)), ("d768_m32", (16, 128))])
 def test_cta_latency_kernel_parity(name, efs):
-    """Calls with at most two queries per SM run one query per CTA of 4 warps (search_knn2_cta_kernel, option search_cta,
-    default on for 32-d / 128-d rows): same ids, sims and counts as the oracle; also with the option off."""
+    """Option search_cta = 1: calls with at most two queries per SM run one query per CTA of 4 warps (search_knn2_cta_kernel,
+    32-d / 128-d rows): same ids, sims and counts as the oracle; and the same again with the option back off."""
     c = case(name)
     dev = device_index(name)
     dev.set_option("search_cta", 1)
@@ -100,7 +100,6 @@ def test_cta_latency_kernel_parity(name, efs):
     ok = ost[:, 3] == 0
     ids, sims, counts = dev.search_batch(q, 10, ef=efs[-1])
     assert np.array_equal(counts, ocounts) and np.array_equal(ids[ok], oids[ok])
-    dev.set_option("search_cta", 1)
 
 
 @pytest.mark.parametrize("name", ["cfg1_10k_d32_m5", "d128_m16"])

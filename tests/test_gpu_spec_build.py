@@ -38,7 +38,7 @@ def test_spec_build_equals_oracle_graph(name, n):
         orc = c["oracle"]
     dev = r.DeviceIndex(c["dim"], c["m"], c["efc"])
     assert dev.add_batch(x, levels, mode=r.BUILD_SPEC) == 0
-    _assert_same_graph(dev.export_graph(), go)
+    _assert_same_graph(dev.export_graph(), go, x=x)   # cfg3: nodes 270 and 4615 tie exactly in the list of node 4693
     p, op = dev.params(), orc.params()
     for key in ("node_count", "max_layer", "enterpoint"):
         assert p[key] == op[key], key
