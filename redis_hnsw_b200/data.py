@@ -52,6 +52,7 @@ def brute_force_topk(x, q, k, device=None, block=4096):
         xt = torch.from_numpy(x).to(device)
         xn = (xt * xt).sum(1)
         out = np.empty((q.shape[0], k), dtype=np.int64)
+        block = max(16, min(block, (1 << 31) // max(1, x.shape[0])))   # the [block, n] distance matrix stays under 8 GiB
         for s in range(0, q.shape[0], block):
             qt = torch.from_numpy(q[s:s + block]).to(device)
             d = xn[None, :] - 2.0 * (qt @ xt.T)
