@@ -26,7 +26,12 @@
 static int DIM, M, EFC;
 static std::vector<float> V;
 static std::vector<int> LEVEL;
-static std::vector<std::vector<std::vector<uint32_t>>> NB;  // [node][level]
+typedef std::vector<std::vector<std::vector<uint32_t>>> GraphT;
+static GraphT NB_true, NB_snap;                              // [node][level]; the snapshot is what speculative runs see
+static GraphT* GP = &NB_true;
+#define NB (*GP)
+// content of every row an insert writes, as it was BEFORE the insert touched it (verify mode: undo + diffs)
+static std::unordered_map<uint64_t, std::vector<uint32_t>>* OLD = nullptr;
 static int max_layer = 0;
 static uint32_t entry = 0;
 
@@ -59,6 +64,9 @@ struct Log {
 };
 static Log* LOG = nullptr;
 static inline uint64_t key(uint32_t node, int lvl) { return ((uint64_t)lvl << 32) | node; }
+static inline void remember(uint32_t node, int lvl) {
+  if (OLD && !OLD->count(key(node, lvl))) (*OLD)[key(node, lvl)] = NB[node][lvl];
+}
 
 static std::vector<uint32_t> stamp;
 static uint32_t epoch = 0;
@@ -106,12 +114,12 @@ static void log_strict(uint32_t node, int lvl, int kind = 0) {
 
 static void add_nb(uint32_t a, int lvl, uint32_t b) {
   auto& l = NB[a][lvl];
-  if (std::find(l.begin(), l.end(), b) == l.end()) l.push_back(b), log_write(a, lvl, {b}, 1);
+  if (std::find(l.begin(), l.end(), b) == l.end()) remember(a, lvl), l.push_back(b), log_write(a, lvl, {b}, 1);
 }
 static void rm_nb(uint32_t a, int lvl, uint32_t b) {
   auto& l = NB[a][lvl];
   auto it = std::find(l.begin(), l.end(), b);
-  if (it != l.end()) l.erase(it), log_write(a, lvl, {b}, 2);
+  if (it != l.end()) remember(a, lvl), l.erase(it), log_write(a, lvl, {b}, 2);
 }
 
 static uint64_t n_reprunes = 0;
@@ -144,6 +152,7 @@ static void reprune(uint32_t e, int lvl, int cap) {
     if (std::find(old.begin(), old.end(), n) == old.end()) add.push_back(n);
   std::vector<uint32_t> nl = keep;
   nl.insert(nl.end(), add.begin(), add.end());
+  remember(e, lvl);
   NB[e][lvl] = nl;
   std::vector<uint32_t> d = add;
   d.insert(d.end(), rem.begin(), rem.end());
@@ -167,13 +176,155 @@ static void insert(uint32_t q) {
     size_t n_sel = std::min<size_t>(w.size(), M);
     std::vector<uint32_t> sel;
     for (size_t i = 0; i < n_sel; ++i) sel.push_back(w[i].second);
+    remember(q, lc);
     NB[q][lc] = sel;
     log_write(q, lc, sel);
-    for (uint32_t r : sel) log_strict(r, lc, 3), add_nb(r, lc, q);
+    for (uint32_t r : sel) log_strict(r, lc, 5), add_nb(r, lc, q);   // 5: append with a cap check after it (core.rs:561)
     for (uint32_t e : sel)
       if ((int)NB[e][lc].size() > cap) reprune(e, lc, cap);
   }
   if (l > l_max) max_layer = l, entry = q;
+}
+
+
+// ---------------------------------------------------------------- verify mode: is the validation criterion SOUND?
+// SIM_VERIFY=B: for windows of B inserts, every insert is executed twice — speculatively against the graph as it stood at
+// the window start (what the device's K1 sees), and in stream order (the truth).  For each criterion: whenever it calls the
+// speculative execution valid, the speculative writes must BE the true writes.  Prints violations (must be 0) and how many
+// inserts each criterion accepts.
+struct Run {
+  Log log;
+  std::unordered_map<uint64_t, std::vector<uint32_t>> before, after;
+};
+
+static void run_insert(uint32_t q, GraphT* g, Run& r, bool undo) {
+  GP = g;
+  LOG = &r.log;
+  OLD = &r.before;
+  const int ml = max_layer;
+  const uint32_t en = entry;
+  insert(q);
+  for (auto& kv : r.before) r.after[kv.first] = NB[(uint32_t)kv.first][kv.first >> 32];
+  if (undo) {
+    for (auto& kv : r.before) NB[(uint32_t)kv.first][kv.first >> 32] = kv.second;
+    NB[q].clear();
+    max_layer = ml, entry = en;
+  }
+  LOG = nullptr;
+  OLD = nullptr;
+  GP = &NB_true;
+}
+
+static int verify(size_t n, const std::vector<size_t>& cps, int B) {
+  stamp.assign(n, 0);
+  NB[0].resize(1);
+  size_t next = 1;
+  for (size_t cp : cps) {
+    for (; next < cp && next < n; ++next) insert((uint32_t)next);
+    size_t accepted[3] = {0, 0, 0}, violations[3] = {0, 0, 0}, total = 0, prefix_sum[3] = {0, 0, 0};
+    const int windows = 12;
+    for (int wdx = 0; wdx < windows && next + B < n; ++wdx) {
+      NB_snap = NB_true;
+      std::vector<Run> truth;
+      std::vector<uint32_t> ids;
+      bool open[3] = {true, true, true};
+      size_t pre[3] = {0, 0, 0};
+      while ((int)ids.size() < B && next < n) {
+        const uint32_t q = (uint32_t)next++;
+        if (LEVEL[q] > max_layer) {   // raises max_layer: ends the window on the device; here it simply runs alone
+          insert(q);
+          NB_snap = NB_true;
+          truth.clear();
+          ids.clear();
+          for (int c = 0; c < 3; ++c) open[c] = true, pre[c] = 0;
+          continue;
+        }
+        Run spec, tru;
+        NB_snap[q].clear();
+        run_insert(q, &NB_snap, spec, true);
+        run_insert(q, &NB_true, tru, false);
+        // conflicts of the speculative reads with the true writes of the earlier inserts of the window
+        bool conflict[3] = {false, false, false};   // coarse | fine | fine + op-log
+        for (const Read& rd : spec.log.reads)
+          for (size_t j = 0; j < truth.size(); ++j) {
+            auto bj = truth[j].before.find(rd.row);
+            if (bj == truth[j].before.end()) continue;
+            const auto& before = bj->second;
+            const auto& after = truth[j].after[rd.row];
+            std::vector<uint32_t> changed;
+            for (uint32_t x : after) if (std::find(before.begin(), before.end(), x) == before.end()) changed.push_back(x);
+            const size_t n_added = changed.size();
+            for (uint32_t x : before) if (std::find(after.begin(), after.end(), x) == after.end()) changed.push_back(x);
+            if (changed.empty()) continue;
+            conflict[0] = true;
+            bool fine_hit = true, op_hit = true;
+            if (rd.kind == 1 || rd.kind == 2) {
+              fine_hit = rd.thr == -INFINITY;
+              for (size_t c = 0; c < changed.size() && !fine_hit; ++c) {
+                if (changed[c] == rd.qnode) continue;
+                const float sv = sim(rd.qnode, changed[c]);
+                fine_hit = rd.kind == 1 ? sv > rd.thr : sv >= rd.thr;
+              }
+              op_hit = fine_hit;
+            } else if (rd.kind == 3 || rd.kind == 4) {
+              op_hit = false;                       // append / remove of one id on a row others only appended to or removed from
+            } else if (rd.kind == 5) {              // append followed by the cap check: the decision must not change
+              const int lvl = (int)(rd.row >> 32);
+              const size_t cap = lvl == 0 ? 2 * M : M;
+              const size_t snap_len = NB_snap[(uint32_t)rd.row][lvl].size();   // (restored by the undo)
+              const size_t true_len = tru.before.count(rd.row) ? tru.before[rd.row].size() : snap_len;
+              op_hit = (snap_len + 1 > cap) != (true_len + 1 > cap);
+              (void)n_added;
+            }
+            if (fine_hit) conflict[1] = true;
+            if (op_hit) conflict[2] = true;
+          }
+        // what did the two executions write?
+        bool same_content = spec.after.size() == tru.after.size();
+        for (auto& kv : spec.after)
+          if (same_content && (!tru.after.count(kv.first) || tru.after[kv.first] != kv.second)) same_content = false;
+        // op-log equality: the same ids added and removed on every row (the base row may differ), same content where a row
+        // was REPLACED (the insert's own rows, re-selected rows)
+        bool same_ops = spec.after.size() == tru.after.size();
+        for (auto& kv : spec.after) {
+          if (!same_ops) break;
+          if (!tru.after.count(kv.first)) { same_ops = false; break; }
+          auto diff = [](const std::vector<uint32_t>& a, const std::vector<uint32_t>& b) {
+            std::vector<uint32_t> d;
+            for (uint32_t x : b) if (std::find(a.begin(), a.end(), x) == a.end()) d.push_back(x);
+            for (uint32_t x : a) if (std::find(b.begin(), b.end(), x) == b.end()) d.push_back(x | 0x80000000u);
+            std::sort(d.begin(), d.end());
+            return d;
+          };
+          if (diff(spec.before[kv.first], kv.second) != diff(tru.before[kv.first], tru.after[kv.first])) same_ops = false;
+        }
+        bool replaced_same = true;
+        for (const Write& w : tru.log.writes)
+          if (w.op == 0 && (!spec.after.count(w.row) || spec.after[w.row] != tru.after[w.row])) replaced_same = false;
+        for (const Write& w : spec.log.writes)
+          if (w.op == 0 && (!tru.after.count(w.row) || spec.after[w.row] != tru.after[w.row])) replaced_same = false;
+        ++total;
+        for (int c = 0; c < 3; ++c) {
+          if (conflict[c]) { open[c] = false; continue; }
+          ++accepted[c];
+          if (open[c]) ++pre[c];
+          const bool ok = c < 2 ? same_content : (same_ops && replaced_same);
+          if (!ok) {
+            ++violations[c];
+            if (violations[c] <= 3) printf("  VIOLATION criterion %d at insert %u (window position %zu)\n", c, q, ids.size());
+          }
+        }
+        truth.push_back(std::move(tru));
+        ids.push_back(q);
+      }
+      for (int c = 0; c < 3; ++c) prefix_sum[c] += pre[c];
+    }
+    printf("N=%zu B=%d inserts=%zu | accepted coarse %zu fine %zu fine+oplog %zu | violations %zu %zu %zu | mean prefix %.1f %.1f %.1f\n", cp, B,
+           total, accepted[0], accepted[1], accepted[2], violations[0], violations[1], violations[2], (double)prefix_sum[0] / windows,
+           (double)prefix_sum[1] / windows, (double)prefix_sum[2] / windows);
+    fflush(stdout);
+  }
+  return 0;
 }
 
 int main(int argc, char** argv) {
@@ -198,6 +349,7 @@ int main(int argc, char** argv) {
   }
   LEVEL[0] = 0;
   NB.resize(n);
+  if (getenv("SIM_VERIFY")) return verify(n, cps, atoi(getenv("SIM_VERIFY")));
   stamp.assign(n, 0);
   NB[0].resize(1);
   const size_t WMAX = 2048;
@@ -244,9 +396,9 @@ int main(int argc, char** argv) {
               if (it == wr.end()) continue;
               for (auto& jw : it->second) {
                 bool hit = true;
-                if (oplog && r.kind == 3 && jw.second->op == 1) hit = false;        // two appends commute (no cap crossing: see header)
+                if (oplog && (r.kind == 3 || r.kind == 5) && jw.second->op == 1) hit = false;   // two appends commute (no cap crossing: see header)
                 else if (oplog && r.kind == 4 && jw.second->op != 0) hit = false;   // remove of one id vs append / remove of another
-                else if (oplog && (r.kind == 3 || r.kind == 4)) hit = true;
+                else if (oplog && (r.kind == 3 || r.kind == 4 || r.kind == 5)) hit = true;
                 else if (fine && (r.kind == 1 || r.kind == 2)) {
                   hit = false;
                   if (r.thr == -INFINITY) hit = true;
