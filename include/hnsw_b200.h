@@ -208,7 +208,8 @@ int hnsw_index_build_stats(hnsw_index_t* idx, uint64_t* out4);
  * [3] distance evaluations  [4] FAST: over-full rows that did not fit the re-prune worklist  [5] FAST: re-prunes skipped
  * [6] FAST: edges refused because a hub row was full  [7] SPEC: commit rounds  [8] SPEC: executions (first + repeated)
  * [9] SPEC: distance evaluations of thrown-away executions  [10] SPEC: inserts sent to the one-warp EXACT kernel
- * [11] SPEC: largest window. */
+ * [11] SPEC: largest window  [12] SPEC: rows committed as append / remove operations on content newer than the
+ * insert's snapshot (dependency-level validation). */
 int hnsw_index_build_stats_ex(hnsw_index_t* idx, uint64_t* out, uint32_t cap, uint32_t* n);
 
 const char* hnsw_last_error(void);

@@ -449,8 +449,11 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   const uint32_t lcap = list_capacity(g.W);
   const bool staged_kind = kind == kKindR1 || kind == kKindR4 || kind == kKindR24;
   const int S = dim <= 128 ? 32 : 8;  // ExactStage<C>::S
-  const uint32_t vis_slots = 8192, wmaxe = 256, rcap = 2048, wcap = 8192, ring = 1024;
-  const size_t list_words = (size_t)((m + 31) & ~31u) + 5 * (size_t)lcap + g.W + 2 * (size_t)wmaxe;
+  const bool fine = opt_spec_validation != 1;
+  // per slot: read records, words of row ids behind them (~350 reads of ~25 ids per insert; twice that with upper levels),
+  // operations, write-log entries and words
+  const uint32_t vis_slots = 8192, wmaxe = 256, rmax = 2048, rcap = fine ? 49152 : 32, ocap = 512, wcap = 8192, ring = 1024;
+  const size_t list_words = (size_t)((m + 31) & ~31u) + 5 * (size_t)lcap + g.W + 3 * (size_t)wmaxe;
   const size_t smem = warp2_smem_bytes(dim, S, vis_slots, 4) + ((kLookaheadInBuilders && (kind == kKindR1 || kind == kKindR4)) ? la_smem_bytes(dim) : 0) +
                       list_words * 4;
   const bool small = m_max_0 <= 64;
@@ -468,21 +471,31 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   const uint32_t resident = (uint32_t)std::min<uint64_t>(ring, (uint64_t)occ * num_sms);
 
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t o_ctl = 0, o_hdr = al(kSpecCtlWords * 4), o_rd = o_hdr + al((size_t)ring * kSpecHdrWords * 4),
-               o_wkey = o_rd + al((size_t)ring * rcap * 4), o_woff = o_wkey + al((size_t)ring * wmaxe * 4),
+  const size_t o_ctl = 0, o_hdr = al(kSpecCtlWords * 4), o_rdh = o_hdr + al((size_t)ring * kSpecHdrWords * 4),
+               o_rdo = o_rdh + al((size_t)ring * rmax * 16), o_rd = o_rdo + al((size_t)ring * rmax * 4),
+               o_okey = o_rd + al((size_t)ring * rcap * 4), o_oval = o_okey + al((size_t)ring * ocap * 4),
+               o_wkey = o_oval + al((size_t)ring * ocap * 4), o_woff = o_wkey + al((size_t)ring * wmaxe * 4),
                o_wdata = o_woff + al((size_t)ring * wmaxe * 4), total = o_wdata + al((size_t)ring * wcap * 4);
+  // K2: one list buffer per warp
+  const int k2_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)lcap * 4)));
+  const size_t k2_smem = (size_t)k2_warps * lcap * 4;
+  if (k2_smem > 48 * 1024) cudaFuncSetAttribute(spec_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem);
   int rc = ensure_scratch(s_spec, total);
   if (rc) return rc;
   char* base = (char*)s_spec.p;
-  cudaError_t e = cudaMemsetAsync(base, 0, o_rd, stream);  // control words + slot headers
+  cudaError_t e = cudaMemsetAsync(base, 0, o_rdh, stream);  // control words + slot headers
   if (e != cudaSuccess) return cuda_fail(e, "spec memset");
   SpecArgs a{};
   a.ring = ring;
   a.m = m, a.cap0 = m_max_0, a.capU = m_max, a.efc = ef_construction, a.lcap = lcap, a.vis_slots = vis_slots;
-  a.rcap = rcap, a.wcap = wcap, a.wmaxe = wmaxe;
+  a.rcap = rcap, a.wcap = wcap, a.wmaxe = wmaxe, a.rmax = rmax, a.ocap = ocap, a.fine = fine ? 1u : 0u;
   a.ctl = (uint32_t*)(base + o_ctl);
   a.hdr = (uint32_t*)(base + o_hdr);
+  a.rdh = (uint4*)(base + o_rdh);
+  a.rdo = (uint32_t*)(base + o_rdo);
   a.rd = (uint32_t*)(base + o_rd);
+  a.okey = (uint32_t*)(base + o_okey);
+  a.oval = (uint32_t*)(base + o_oval);
   a.wkey = (uint32_t*)(base + o_wkey);
   a.woff = (uint32_t*)(base + o_woff);
   a.wdata = (uint32_t*)(base + o_wdata);
@@ -491,7 +504,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   const uint32_t end = first + count;
   double ema = 4.0;  // committed inserts per round
   uint32_t h[kSpecCtlWords];
-  uint32_t prev_exec = 0, prev_dist = 0, prev_repr = 0, prev_waste = 0;
+  uint32_t prev_exec = 0, prev_dist = 0, prev_repr = 0, prev_waste = 0, prev_oprows = 0;
   const bool trace = std::getenv("HNSW_BUILD_TRACE") != nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double k1_ms = 0, k2_ms = 0, host_ms = 0;
@@ -522,7 +535,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     if (e != cudaSuccess) return cuda_fail(e, "spec_exec launch");
     if (trace) cudaEventRecord(ev[1], stream);
     g_launches++;
-    spec_commit_kernel<<<1, 256, 0, stream>>>(g, a);
+    spec_commit_kernel<<<1, 32 * k2_warps, k2_smem, stream>>>(g, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "spec_commit launch");
     if (trace) cudaEventRecord(ev[2], stream);
@@ -549,10 +562,12 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     build_stats_ex[8 - 4] += h[kSpecExecuted] - prev_exec;
     build_stats_ex[9 - 4] += h[kSpecDistWasted] - prev_waste;
     build_stats_ex[11 - 4] = std::max<uint64_t>(build_stats_ex[11 - 4], B);
+    build_stats_ex[12 - 4] += h[kSpecOpRows] - prev_oprows;
+    prev_oprows = h[kSpecOpRows];
     prev_exec = h[kSpecExecuted], prev_dist = h[kSpecDistEvals], prev_repr = h[kSpecReprunesDone], prev_waste = h[kSpecDistWasted];
-    if (trace && (build_stats_ex[7 - 4] % 1024) == 0) {
-      std::fprintf(stderr, "[spec] f=%u window=%u committed=%u reason=%u ema=%.1f | last 1024 rounds: K1 %.3f ms, K2 %.3f ms, round (host clock) %.3f ms\n",
-                   f, B, committed, reason, ema, k1_ms / 1024, k2_ms / 1024, host_ms / 1024);
+    if (trace && (build_stats_ex[7 - 4] % 128) == 0) {
+      std::fprintf(stderr, "[spec] f=%u window=%u committed=%u reason=%u ema=%.1f | last 128 rounds: K1 %.3f ms, K2 %.3f ms, round (host clock) %.3f ms\n",
+                   f, B, committed, reason, ema, k1_ms / 128, k2_ms / 128, host_ms / 128);
       k1_ms = k2_ms = host_ms = 0;
       // where and for how long every warp of this round's K1 ran (slot headers still hold the round's diagnostics)
       std::vector<uint32_t> hh((size_t)ring * kSpecHdrWords);
@@ -810,8 +825,8 @@ int hnsw_index_build_stats(hnsw_index_t* idx, uint64_t* out4) {
 
 int hnsw_index_build_stats_ex(hnsw_index_t* idx, uint64_t* out, uint32_t cap, uint32_t* n) {
   IDX_OR_FAIL(idx)
-  if (n) *n = 12;
-  for (uint32_t i = 0; i < 12 && i < cap; ++i) out[i] = i < 4 ? ix.build_stats[i] : ix.build_stats_ex[i - 4];
+  if (n) *n = 13;
+  for (uint32_t i = 0; i < 13 && i < cap; ++i) out[i] = i < 4 ? ix.build_stats[i] : ix.build_stats_ex[i - 4];
   return HNSW_OK;
 }
 

@@ -48,8 +48,8 @@ struct Index {
   uint64_t rng_state = 0x9E3779B97F4A7C15ull;
   uint64_t build_stats[4] = {0, 0, 0, 0};
   // [4] wl dropped [5] re-prunes skipped [6] edges refused [7] spec rounds [8] spec executions [9] spec wasted evals
-  // [10] spec exact fallbacks [11] spec largest window   (hnsw_index_build_stats_ex)
-  uint64_t build_stats_ex[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // [10] spec exact fallbacks [11] spec largest window [12] spec rows committed as operations   (hnsw_index_build_stats_ex)
+  uint64_t build_stats_ex[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   // options / adaptive state
   uint32_t opt_vis_slots = 0;
@@ -77,6 +77,7 @@ struct Index {
   uint32_t* d_ver0 = nullptr;     // [cap_nodes] SPEC builder row stamps: 1 + id of the last insert that wrote the row
   uint32_t* d_verU = nullptr;     // [cap_upper]
   uint32_t opt_spec_window = 0;   // SPEC: fixed window size (0 = adaptive)
+  int opt_spec_validation = 0;    // SPEC: 0 / 2 = dependency-level validation (spec.cuh), 1 = row-level (the round-2 first version; kept for A/B)
   uint32_t opt_spec_mult = 0;     // SPEC: adaptive window = mult / 10 x (inserts committed per round, running mean); 0 = 30 (3.0x: best of 1.5x .. 8x at 1M nodes, profiles/r2_spec_build.md)
 
   // scratch

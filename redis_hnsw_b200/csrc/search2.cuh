@@ -413,7 +413,9 @@ __device__ __forceinline__ void expand_chunk2(const Graph& g, Warp2<C, S, T>& w,
 
 // observer of the rows a search expands (the SPEC builder logs them as its read set, spec.cuh); the default does nothing
 struct NoSearchHook {
-  __device__ __forceinline__ void expand(uint32_t, uint32_t) const {}
+  __device__ __forceinline__ void expand(uint32_t, uint32_t, float) const {}   // (node, level, admission threshold of the moment)
+  __device__ __forceinline__ void ids(uint32_t) const {}                       // a chunk of the row's ids, one per lane (kEmpty = none)
+  __device__ __forceinline__ void done() const {}
 };
 
 // core.rs:607-675
@@ -437,11 +439,12 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
     uint32_t* ovf;
     const uint32_t* row = row_ptr(g, cid, level, &ovf);          // core.rs:642-645
     if (!row) continue;
-    hook.expand(cid, level);
+    hook.expand(cid, level, L.worst);
     bool more = true;
     for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
       const uint32_t nb = row[c * 32 + lane];
       more = __shfl_sync(kFull, nb, 31) != kEmpty;               // rows are compact: an empty tail ends the list
+      hook.ids(nb);
       expand_chunk2<EFR, C, S, T, COPY>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
     }
     if (more) {                                                  // overflow rows (degree is unbounded); rare
@@ -450,9 +453,11 @@ __device__ __forceinline__ void search_layer2(const Graph& g, Warp2<C, S, T>& w,
         uint32_t nb = g.pool[(size_t)link * 32 + lane];
         link = __shfl_sync(kFull, nb, 31);
         if (lane == 31) nb = kEmpty;
+        hook.ids(nb);
         expand_chunk2<EFR, C, S, T, COPY>(g, w, nb, ef, L, cnt, adj_prefetch, lane);
       }
     }
+    hook.done();
   }
   L.finish(lane);                                                // wide lists: back to the sorted layout (search.cuh)
 }

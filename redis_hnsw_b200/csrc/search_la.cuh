@@ -132,7 +132,8 @@ __device__ __forceinline__ void search_layer2_la(const Graph& g, Warp2<C, S, T>&
     uint32_t* ovf;
     const uint32_t* row = row_ptr(g, cid, level, &ovf);          // core.rs:642-645
     if (!row) continue;
-    hook.expand(cid, level);
+    hook.expand(cid, level, L.worst);   // (the ids of the row are not handed to the hook here: see spec.cuh)
+    hook.done();
     uint32_t nb, newmask;
     bool more;
     int buf;

@@ -7,23 +7,39 @@
 //                            committed, nothing else is — WITHOUT writing to it: new row contents go to a private write
 //                            log (read back by the insert itself: read-your-own-writes), and every graph row the insert
 //                            looked at goes to a read log.
-//   K2  spec_commit_kernel   one CTA walks the window in order.  Insert q commits iff no row of its read log was written
+//   K2  spec_commit_kernel   one CTA walks the window in order.  Insert q commits iff nothing it DEPENDED on was written
 //                            since its snapshot (row stamps: ver[row] = 1 + id of the last insert that wrote the row).  A
-//                            valid insert saw exactly the rows the sequential execution would have seen, and the insert is a
-//                            deterministic function of those rows, so its write log IS the sequential result; it is copied
-//                            into the graph and the rows are stamped.  The walk stops at the first invalid insert, which is
-//                            re-executed by the next K1 (now as the head of its window, where it cannot fail again).
-//   Inserts that were executed but not reached keep their logs; the next K1 re-validates them against the stamps and only
-//   re-executes the ones that lost a row.
+//                            valid insert took every decision the sequential execution would have taken, and the insert is a
+//                            deterministic function of those decisions, so its write log IS the sequential result; it is
+//                            applied to the graph and the rows are stamped.  The walk stops at the first invalid insert,
+//                            which is re-executed by the next K1 (now as the head of its window, where it cannot fail).
+//   Inserts that were executed but not reached keep their logs; the next K1 re-validates them and only re-executes the
+//   ones that lost a dependency.
 //
-// Exactness does not rest on any probability: an insert is committed only when its whole read set is untouched.  What
-// speculation buys is measured (tools/sim_spec_build.cpp): the dependency chains between consecutive
-// inserts are dense (every insert rewrites ~46 rows and reads ~350), so a round commits a prefix of O(sqrt N)-ish inserts.
+// What "depended on" means (a.fine; a.fine = 0 is row-level validation: any write to any row the insert touched):
+//   search read   (kind 1)  a row expanded by search_level with the admission threshold of that moment (core.rs:657) and
+//                           the ids it held.  A later write to the row matters only if an id that came or went could have
+//                           been admitted: sim(q, id) above the threshold (the threshold only rises during a search).
+//   sweep read    (kind 2)  a row swept by a re-selection of e (core.rs:698-721), with the sim of the last selected id.
+//   strict read   (kind 0)  the row a re-selection replaces: its whole content decides the outcome.
+//   length bound  (kind 6)  a row that got the new node appended and still fit its cap (core.rs:561): the row may have
+//                           grown meanwhile, as long as the check still says "fits".
+//   Appends and removals of one id (core.rs:137-152) are logged as OPERATIONS besides the new row content; at commit a
+//   row that was not written since the snapshot takes the content, a row that was takes the operations, applied to what
+//   it holds now — which is what the sequential execution does.  (Whether the id is present cannot have changed: it is
+//   only ever added or removed together with a write to the strict row of the same re-selection.)
+//   tools/sim_spec_build.cpp (SIM_VERIFY) replays these rules on the CPU: every accepted execution equals the sequential one.
+//
+// Exactness does not rest on any probability: the sims of validation are compared with a margin far above f32 rounding,
+// so an insert is committed only when every decision it took is provably the sequential one.  What speculation buys is
+// measured (tools/sim_spec_build.cpp): a round commits a prefix of O(sqrt N)-ish inserts.
 #pragma once
 #include "build2.cuh"
 #include "search_la.cuh"
 
 namespace hnsw {
+
+static_assert(!kLookaheadInBuilders, "search_layer2_la does not report row ids to the search hook: the SPEC read log needs them");
 
 enum SpecHdr : int {
   kSpecState = 0,     // 0 = needs execution, 1 = executed (logs valid for `snap`)
@@ -37,9 +53,12 @@ enum SpecHdr : int {
   kSpecT0 = 8,        // diagnostics: %globaltimer (low word, ns) when the warp entered K1,
   kSpecDur = 9,       //              ns it spent there,
   kSpecSm = 10,       //              SM it ran on | 0x80000000 when it executed (not just validated)
+  kSpecOps = 11,      // operations logged (fine validation)
   kSpecHdrWords = 12,
 };
-constexpr uint32_t kSpecRdOverflow = 1, kSpecWrOverflow = 2;
+constexpr uint32_t kSpecRdOverflow = 1, kSpecWrOverflow = 2, kSpecOpOverflow = 4;
+// read kinds (word y of a read record = kind | len << 3)
+constexpr uint32_t kRdStrict = 0, kRdSearch = 1, kRdSweep = 2, kRdLenBound = 6;
 
 enum SpecCtl : int {
   kSpecCommitted = 0,  // inserts committed by this K2
@@ -52,6 +71,7 @@ enum SpecCtl : int {
   kSpecMaxLayer = 7,
   kSpecEntry = 8,
   kSpecError = 9,
+  kSpecOpRows = 10,    // rows committed as operations on newer content (accumulates)
   kSpecCtlWords = 16,
 };
 
@@ -61,8 +81,14 @@ struct SpecArgs {
   uint32_t ring;       // slots (power of two); slot = id & (ring - 1)
   uint32_t m, cap0, capU, efc, lcap, vis_slots;
   uint32_t rcap, wcap, wmaxe;
+  uint32_t rmax, ocap; // read records / operations per slot
+  uint32_t fine;       // 1 = dependency-level validation (see header), 0 = row-level
   uint32_t* hdr;       // [ring][kSpecHdrWords]
-  uint32_t* rd;        // [ring][rcap]   row keys
+  uint4* rdh;          // [ring][rmax]   read records {row key, kind | len << 3, query node | base length, threshold | growth}
+  uint32_t* rdo;       // [ring][rmax]   offset of the record's ids in rd
+  uint32_t* rd;        // [ring][rcap]   ids the rows held when they were read (kinds 1, 2)
+  uint32_t* okey;      // [ring][ocap]   operations in program order: row key,
+  uint32_t* oval;      // [ring][ocap]   id to append, or id | 0x80000000 to remove
   uint32_t* wkey;      // [ring][wmaxe]  row key of entry e (kEmpty = dead)
   uint32_t* woff;      // [ring][wmaxe]  word offset of entry e in wdata: {reserved, len, ids...}
   uint32_t* wdata;     // [ring][wcap]
@@ -78,19 +104,90 @@ __device__ __forceinline__ uint32_t spec_ver(const SpecArgs& a, uint32_t key) {
 // ---------------------------------------------------------------- per-warp logs
 
 struct SpecLog {
+  uint4* rdh;          // global
+  uint32_t* rdo;       // global
   uint32_t* rd;        // global
   uint32_t* wdata;     // global
+  uint32_t* okey;      // global
+  uint32_t* oval;      // global
   uint32_t* wkey_s;    // shared [wmaxe]
   uint32_t* woff_s;    // shared [wmaxe]
-  uint32_t rcap, wcap, wmaxe;
-  uint32_t n_reads, n_entries, used, flags;  // warp-uniform
+  uint32_t* wbase_s;   // shared [wmaxe]  length of the row in the graph when the entry was made
+  uint32_t rmax, rcap, wcap, wmaxe, ocap, fine, self;
+  uint32_t n_reads, rused, n_entries, used, n_ops, flags;  // warp-uniform
+  uint32_t cur_key, cur_kind, cur_aux, cur_off;             // record being written (begin .. end)
+  float cur_thr;
+  bool cur_open;
 
-  __device__ __forceinline__ void read(uint32_t key, int lane) {
-    if (n_reads < rcap) {
-      if (lane == 0) rd[n_reads] = key;
+  // a record without ids (strict read, length bound)
+  __device__ __forceinline__ void read_plain(uint32_t key, uint32_t kind, uint32_t aux, uint32_t w, int lane) {
+    if (n_reads < rmax) {
+      if (lane == 0) rdh[n_reads] = make_uint4(key, kind, aux, w), rdo[n_reads] = 0;
       ++n_reads;
     } else {
       flags |= kSpecRdOverflow;
+    }
+  }
+  // a record with the ids of the row: begin, ids (chunks of <= 32, kEmpty = no id), end
+  __device__ __forceinline__ void begin(uint32_t key, uint32_t kind, uint32_t aux, float thr) {
+    cur_key = key, cur_kind = kind, cur_aux = aux, cur_thr = thr, cur_off = rused;
+    cur_open = n_reads < rmax;
+    if (!cur_open) flags |= kSpecRdOverflow;
+  }
+  __device__ __forceinline__ void ids(uint32_t nb, int lane) {
+    if (!cur_open || !fine) return;
+    const uint32_t mask = __ballot_sync(kFull, nb != kEmpty);
+    const uint32_t n = __popc(mask);
+    if (rused + n > rcap) {
+      flags |= kSpecRdOverflow;
+      cur_open = false;
+      return;
+    }
+    if (nb != kEmpty) rd[rused + __popc(mask & ((1u << lane) - 1u))] = nb;
+    rused += n;
+  }
+  __device__ __forceinline__ void end(int lane) {
+    if (!cur_open) return;
+    if (lane == 0) rdh[n_reads] = make_uint4(cur_key, cur_kind | ((rused - cur_off) << 3), cur_aux, __float_as_uint(cur_thr)), rdo[n_reads] = cur_off;
+    ++n_reads;
+    cur_open = false;
+  }
+  // the row of (node, level) as the graph holds it -> one record (K1 never writes the graph: the same at any time)
+  __device__ __forceinline__ void read_row(const Graph& g, uint32_t node, uint32_t level, uint32_t key, uint32_t kind, uint32_t aux,
+                                           float thr, int lane) {
+    begin(key, kind, aux, thr);
+    uint32_t* ovf;
+    const uint32_t* row = row_ptr(g, node, level, &ovf);
+    if (row && fine) {
+      bool more = true;
+      for (uint32_t c = 0; c < g.W / 32 && more; ++c) {
+        const uint32_t nb = __ldcg(row + c * 32 + lane);
+        more = __shfl_sync(kFull, nb, 31) != kEmpty;
+        ids(nb, lane);
+      }
+      uint32_t link = more ? __ldcg(ovf) : kEmpty;
+      while (link != kEmpty) {
+        uint32_t nb = __ldcg(g.pool + (size_t)link * 32 + lane);
+        link = __shfl_sync(kFull, nb, 31);
+        if (lane == 31) nb = kEmpty;
+        ids(nb, lane);
+      }
+    }
+    end(lane);
+  }
+  // thresholds of the sweep records [from, n_reads) are known once the re-selection is over
+  __device__ __forceinline__ void patch_thr(uint32_t from, float thr, int lane) {
+    __syncwarp();
+    for (uint32_t i = from + lane; i < n_reads; i += 32)
+      if ((rdh[i].y & 7u) == kRdSweep) rdh[i].w = __float_as_uint(thr);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void op(uint32_t key, uint32_t val, int lane) {
+    if (n_ops < ocap) {
+      if (lane == 0) okey[n_ops] = key, oval[n_ops] = val;
+      ++n_ops;
+    } else {
+      flags |= kSpecOpOverflow;
     }
   }
   // index of the live entry of `key`, or -1
@@ -103,21 +200,27 @@ struct SpecLog {
   }
 };
 
-// hook of search_layer2: every expanded row is a read (core.rs:642-646)
+// hook of search_layer2: every expanded row is a read (core.rs:642-646), with the threshold of the moment and its ids
 struct SpecSearchHook {
   const uint32_t* upper_base;
   SpecLog* lg;
   int lane;
-  __device__ __forceinline__ void expand(uint32_t node, uint32_t level) const {
-    lg->read(level == 0 ? node : (0x80000000u | (upper_base[node] + level - 1)), lane);   // row_key()
+  __device__ __forceinline__ void expand(uint32_t node, uint32_t level, float thr) const {
+    const uint32_t key = level == 0 ? node : (0x80000000u | (upper_base[node] + level - 1));   // row_key()
+    lg->begin(key, lg->fine ? kRdSearch : kRdStrict, lg->self, thr);
   }
+  __device__ __forceinline__ void ids(uint32_t nb) const { lg->ids(nb, lane); }
+  __device__ __forceinline__ void done() const { lg->end(lane); }
 };
 
-// the insert's view of the adjacency list of (node, level): its own latest version, else the graph's (logged as a read)
+// the insert's view of the adjacency list of (node, level): its own latest version, else the graph's.  `ent` = the entry
+// of the write log the list came from, or -1.  Row-level validation logs every row that comes from the graph; the
+// dependency-level one leaves it to the caller to say what the row was read FOR.
 __device__ __forceinline__ uint32_t view_load(const Graph& g, SpecLog& lg, uint32_t node, uint32_t level, uint32_t* buf,
-                                              uint32_t lcap, int lane) {
+                                              uint32_t lcap, int lane, int* ent = nullptr) {
   const uint32_t key = row_key(g, node, level);
   const int e = lg.find(key, lane);
+  if (ent) *ent = e;
   if (e >= 0) {
     const uint32_t* p = lg.wdata + lg.woff_s[e];
     const uint32_t len = p[1];
@@ -126,16 +229,17 @@ __device__ __forceinline__ uint32_t view_load(const Graph& g, SpecLog& lg, uint3
     __syncwarp();
     return len;
   }
-  lg.read(key, lane);
+  if (!lg.fine) lg.read_plain(key, kRdStrict, 0, 0, lane);
   uint32_t* ovf;
   const uint32_t* row = row_ptr(g, node, level, &ovf);
   if (!row) return 0;
   return list_load(g, row, ovf, buf, lcap, lane);
 }
 
-// new content of (node, level) -> write log (in place when the row already has an entry that is large enough)
+// new content of (node, level) -> write log (in place when the row already has an entry that is large enough).
+// `base_len` = what the graph's row held (only used when the entry is new).
 __device__ __forceinline__ void view_store(const Graph& g, SpecLog& lg, uint32_t node, uint32_t level, const uint32_t* buf,
-                                           uint32_t len, int lane) {
+                                           uint32_t len, uint32_t base_len, int lane) {
   const uint32_t key = row_key(g, node, level);
   __syncwarp();
   int e = lg.find(key, lane);
@@ -143,6 +247,7 @@ __device__ __forceinline__ void view_store(const Graph& g, SpecLog& lg, uint32_t
   if (e >= 0 && lg.wdata[lg.woff_s[e]] >= len) {
     off = lg.woff_s[e];
   } else {
+    const uint32_t base = e >= 0 ? lg.wbase_s[e] : base_len;
     if (e >= 0 && lane == 0) lg.wkey_s[e] = kEmpty;            // superseded
     const uint32_t reserve = len + 8;
     if (lg.n_entries >= lg.wmaxe || lg.used + 2 + reserve > lg.wcap) {
@@ -154,6 +259,7 @@ __device__ __forceinline__ void view_store(const Graph& g, SpecLog& lg, uint32_t
     if (lane == 0) {
       lg.wkey_s[lg.n_entries] = key;
       lg.woff_s[lg.n_entries] = off;
+      lg.wbase_s[lg.n_entries] = base;
       lg.wdata[off] = reserve;
     }
     lg.n_entries += 1;
@@ -198,8 +304,12 @@ __device__ __forceinline__ void reprune_select2v(const Graph& g, SpecLog& lg, Wa
     if (np >= 32) flush(32);
   };
   for (uint32_t i = 0; i < n_old; i += 32) feed((i + lane < n_old) ? old[i + lane] : kEmpty);   // core.rs:549-557
+  const uint32_t first_sweep = lg.n_reads;
   for (uint32_t j = 0; j < n_old; ++j) {                         // extend_candidates (core.rs:698-721)
     const uint32_t n_row = view_load(g, lg, old[j], level, tmp, lcap, lane);
+    // what the sweep depends on is the row in the GRAPH (the insert's own edits on top of it are the same in any order);
+    // the new node's own rows have no earlier writer
+    if (lg.fine && old[j] != lg.self) lg.read_row(g, old[j], level, row_key(g, old[j], level), kRdSweep, e, 0.f, lane);
     if (n_row == kEmpty) {
       if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
       continue;
@@ -208,6 +318,99 @@ __device__ __forceinline__ void reprune_select2v(const Graph& g, SpecLog& lg, Wa
   }
   if (np) flush(np);
   L.finish(lane);                                                // wide lists (EFR >= 4): back to the sorted layout
+  if (lg.fine) lg.patch_thr(first_sweep, L.worst, lane);         // -inf while fewer than `cap` candidates exist
+}
+
+// ---------------------------------------------------------------- validation (K1 for kept logs, K2 before a commit)
+
+// sim of two slab rows, any summation order: only ever compared with a margin (spec_read_conflicts)
+__device__ __forceinline__ float spec_sim_loose(const Graph& g, uint32_t a, uint32_t b, int lane) {
+  const float4* x = reinterpret_cast<const float4*>(g.vecs + (size_t)a * g.dim);
+  const float4* y = reinterpret_cast<const float4*>(g.vecs + (size_t)b * g.dim);
+  float acc = 0.f;
+  for (uint32_t i = lane; i < g.dim / 4; i += 32) {
+    const float4 u = __ldg(x + i), v = __ldg(y + i);
+    const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
+    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+  return -acc;
+}
+
+// One warp: the row of read record `h` was written after the snapshot — could that have changed what the insert did?
+// `buf`: `lcap` words of shared memory.  Conservative: true whenever the answer is not a provable no.
+__device__ __forceinline__ bool spec_read_conflicts(const Graph& g, const SpecArgs& a, uint4 h, const uint32_t* ids, uint32_t* buf,
+                                                    int lane) {
+  const uint32_t kind = h.y & 7u, len = h.y >> 3;
+  if (kind == kRdStrict || !a.fine) return true;
+  const uint32_t *row, *ovf;
+  if (h.x & 0x80000000u) {
+    const uint32_t r = h.x & 0x7FFFFFFFu;
+    row = g.adjU + (size_t)r * g.W, ovf = g.ovfU + r;
+  } else {
+    row = g.adj0 + (size_t)h.x * g.W, ovf = g.ovf0 + h.x;
+  }
+  __syncwarp();
+  const uint32_t cur = list_load(g, row, ovf, buf, a.lcap, lane);
+  if (cur == kEmpty) return true;
+  if (kind == kRdLenBound) return cur > h.z + h.w;               // the cap check (core.rs:561) would not say "fits" any more
+  const float thr = __uint_as_float(h.w);
+  if (!(thr > -CUDART_INF_F)) return true;                       // the list was not full: any id would have been admitted
+  // f32 sums of <= 65536 non-negative terms in two different orders differ by far less than 2.5e-4 of their value
+  const float bar = thr - 2.5e-4f * fabsf(thr) - 1e-30f;
+  const uint32_t qn = h.z;
+  bool hit = false;
+  for (uint32_t c = 0; c < len && !hit; c += 32) {               // ids that left the row
+    const uint32_t id = c + lane < len ? __ldcg(ids + c + lane) : kEmpty;
+    bool gone = id != kEmpty && id != qn;
+    for (uint32_t j = 0; j < cur && gone; ++j) gone = buf[j] != id;
+    uint32_t mask = __ballot_sync(kFull, gone);
+    while (mask && !hit) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      hit = spec_sim_loose(g, qn, __shfl_sync(kFull, id, b), lane) > bar;
+    }
+  }
+  for (uint32_t c = 0; c < cur && !hit; c += 32) {               // ids that came
+    const uint32_t id = c + lane < cur ? buf[c + lane] : kEmpty;
+    bool came = id != kEmpty && id != qn;
+    for (uint32_t j = 0; j < len && came; ++j) came = __ldcg(ids + j) != id;
+    uint32_t mask = __ballot_sync(kFull, came);
+    while (mask && !hit) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      hit = spec_sim_loose(g, qn, __shfl_sync(kFull, id, b), lane) > bar;
+    }
+  }
+  return hit;
+}
+
+// One warp walks the read records [first, n_reads) of a slot with stride `step`; true (warp-uniform) = a dependency was lost.
+__device__ __forceinline__ bool spec_reads_conflict(const Graph& g, const SpecArgs& a, uint32_t slot, uint32_t snap, uint32_t n_reads,
+                                                    uint32_t first, uint32_t step, uint32_t* buf, int lane) {
+  const uint4* rdh = a.rdh + (size_t)slot * a.rmax;
+  const uint32_t* rdo = a.rdo + (size_t)slot * a.rmax;
+  const uint32_t* rd = a.rd + (size_t)slot * a.rcap;
+  for (uint32_t i = first; i < n_reads; i += step) {
+    uint4 h = make_uint4(0, 0, 0, 0);
+    uint32_t off = 0;
+    bool stale = false;
+    if (i + lane < n_reads) {
+      h = __ldcg(rdh + i + lane);
+      off = __ldcg(rdo + i + lane);
+      stale = spec_ver(a, h.x) > snap;
+    }
+    if (__any_sync(kFull, stale && ((h.y & 7u) == kRdStrict || !a.fine))) return true;
+    uint32_t mask = __ballot_sync(kFull, stale);
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint4 hb = make_uint4(__shfl_sync(kFull, h.x, b), __shfl_sync(kFull, h.y, b), __shfl_sync(kFull, h.z, b), __shfl_sync(kFull, h.w, b));
+      if (spec_read_conflicts(g, a, hb, rd + __shfl_sync(kFull, off, b), buf, lane)) return true;
+    }
+  }
+  return false;
 }
 
 // ---------------------------------------------------------------- K1
@@ -222,28 +425,11 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   const uint32_t q = a.frontier + blockIdx.x;
   const uint32_t slot = q & (a.ring - 1);
   uint32_t* hdr = a.hdr + (size_t)slot * kSpecHdrWords;
-  uint32_t* rd = a.rd + (size_t)slot * a.rcap;
   uint64_t t_in;
   uint32_t smid;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_in));
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
   if (lane == 0) hdr[kSpecT0] = (uint32_t)t_in, hdr[kSpecDur] = 0, hdr[kSpecSm] = smid;
-
-  // executed earlier and still valid?  (rows stamped after the snapshot invalidate the logs)
-  if (__ldcg(hdr + kSpecState) == 1u && __ldcg(hdr + kSpecNode) == q) {
-    const uint32_t snap = __ldcg(hdr + kSpecSnap), n_reads = __ldcg(hdr + kSpecReads), flags = __ldcg(hdr + kSpecFlags);
-    if (flags & kSpecWrOverflow) return;                          // unusable either way: the host runs it through EXACT
-    // Warp-uniform control flow on purpose: a per-lane early exit from this loop left the warp split into groups that
-    // ran the whole insert below one after the other (measured: 4.1 ms instead of 0.9 ms per execution, r2 call D).
-    bool bad = (flags & kSpecRdOverflow) && snap != q;
-    for (uint32_t i = 0; i < n_reads && !bad; i += 32) {
-      const bool mine = i + lane < n_reads && spec_ver(a, __ldcg(rd + i + lane)) > snap;
-      bad = __any_sync(kFull, mine);
-    }
-    if (!bad) return;
-    if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist]);
-    __syncwarp();
-  }
 
   Warp2<C, S, T> w;
   unsigned char* after = warp2_setup<C, S, T>(w, smem2, a.vis_slots, lane);
@@ -251,20 +437,48 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   LaBuf<C> lb;
   if constexpr (kLookahead) after = la_setup<C, S, T>(lb, w, after, lane);
   uint32_t* lists = reinterpret_cast<uint32_t*>(after);
-  // sel[m] | old[lcap] | keep_add[lcap + W] | rem[lcap] | edit[lcap] | tmp[lcap] | wkey[wmaxe] | woff[wmaxe]
+  // sel[m] | old[lcap] | keep_add[lcap + W] | rem[lcap] | edit[lcap] | tmp[lcap] | wkey[wmaxe] | woff[wmaxe] | wbase[wmaxe]
   uint32_t* sel = lists;
   uint32_t* old = sel + ((a.m + 31) & ~31u);
   uint32_t* keep_add = old + a.lcap;
   uint32_t* rem = keep_add + a.lcap + g.W;
   uint32_t* edit = rem + a.lcap;
   uint32_t* tmp = edit + a.lcap;
+
+  // executed earlier and still valid?  (writes after the snapshot to what the insert depended on void the logs)
+  if (__ldcg(hdr + kSpecState) == 1u && __ldcg(hdr + kSpecNode) == q) {
+    const uint32_t snap = __ldcg(hdr + kSpecSnap), n_reads = __ldcg(hdr + kSpecReads), flags = __ldcg(hdr + kSpecFlags);
+    if (flags & kSpecWrOverflow) return;                          // unusable either way: the host runs it through EXACT
+    // Warp-uniform control flow on purpose: a per-lane early exit from this loop left the warp split into groups that
+    // ran the whole insert below one after the other (measured: 4.1 ms instead of 0.9 ms per execution, r2 call D).
+    bool bad = (flags & kSpecRdOverflow) && snap != q;
+    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, n_reads, 0, 32, tmp, lane);
+    if (!bad && (flags & kSpecOpOverflow)) {                      // operations missing: every written row must be untouched
+      const uint32_t n_entries = __ldcg(hdr + kSpecEntries);
+      const uint32_t* wk = a.wkey + (size_t)slot * a.wmaxe;
+      for (uint32_t i = 0; i < n_entries && !bad; i += 32) {
+        const uint32_t key = i + lane < n_entries ? __ldcg(wk + i + lane) : kEmpty;
+        bad = __any_sync(kFull, key != kEmpty && spec_ver(a, key) > snap);
+      }
+    }
+    if (!bad) return;
+    if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist]);
+    __syncwarp();
+  }
+
   SpecLog lg;
-  lg.rd = rd;
+  lg.rdh = a.rdh + (size_t)slot * a.rmax;
+  lg.rdo = a.rdo + (size_t)slot * a.rmax;
+  lg.rd = a.rd + (size_t)slot * a.rcap;
   lg.wdata = a.wdata + (size_t)slot * a.wcap;
+  lg.okey = a.okey + (size_t)slot * a.ocap;
+  lg.oval = a.oval + (size_t)slot * a.ocap;
   lg.wkey_s = tmp + a.lcap;
   lg.woff_s = lg.wkey_s + a.wmaxe;
-  lg.rcap = a.rcap, lg.wcap = a.wcap, lg.wmaxe = a.wmaxe;
-  lg.n_reads = lg.n_entries = lg.used = lg.flags = 0;
+  lg.wbase_s = lg.woff_s + a.wmaxe;
+  lg.rmax = a.rmax, lg.rcap = a.rcap, lg.wcap = a.wcap, lg.wmaxe = a.wmaxe, lg.ocap = a.ocap, lg.fine = a.fine, lg.self = q;
+  lg.n_reads = lg.rused = lg.n_entries = lg.used = lg.n_ops = lg.flags = 0;
+  lg.cur_open = false;
   SpecSearchHook hook{g.upper_base, &lg, lane};
 
   CandList<EFR> L;
@@ -291,7 +505,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
       if (e < n_sel) sel[e] = L.id[r] & ~kExpanded;
     }
     __syncwarp();
-    view_store(g, lg, q, (uint32_t)lc, sel, n_sel, lane);         // connect_neighbors (core.rs:759-774)
+    view_store(g, lg, q, (uint32_t)lc, sel, n_sel, 0, lane);      // connect_neighbors (core.rs:759-774)
     for (uint32_t i = 0; i < n_sel; ++i) {
       const uint32_t r = sel[i];
       uint32_t len = view_load(g, lg, r, (uint32_t)lc, edit, a.lcap, lane);
@@ -299,26 +513,34 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
         if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
         continue;
       }
+      const uint32_t base_len = len;
       if (list_find(edit, len, q, lane) < 0) {
         if (lane == 0) edit[len] = q;
         ++len;
+        lg.op(row_key(g, r, (uint32_t)lc), q, lane);              // an operation on r, whatever r holds by then
       }
-      view_store(g, lg, r, (uint32_t)lc, edit, len, lane);
+      view_store(g, lg, r, (uint32_t)lc, edit, len, base_len, lane);
     }
     for (uint32_t i = 0; i < n_sel; ++i) {                        // shrink connections (core.rs:540-574), nearest-first
       const uint32_t e = sel[i];
-      const uint32_t n_old = view_load(g, lg, e, (uint32_t)lc, old, a.lcap, lane);
+      int ent;
+      const uint32_t n_old = view_load(g, lg, e, (uint32_t)lc, old, a.lcap, lane, &ent);
       if (n_old == kEmpty) {
         if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
         continue;
       }
-      if (n_old <= cap) continue;                                 // core.rs:561
+      if (n_old <= cap) {                                         // core.rs:561: fits — and keeps fitting while the row
+        if (lg.fine)                                              // in the graph grows by at most cap - n_old ids
+          lg.read_plain(row_key(g, e, (uint32_t)lc), kRdLenBound, ent >= 0 ? lg.wbase_s[ent] : n_old, cap - n_old, lane);
+        continue;
+      }
+      if (lg.fine) lg.read_plain(row_key(g, e, (uint32_t)lc), kRdStrict, 0, 0, lane);   // re-selected: its content decides
       load_q_from_slab<C, S, T>(w, g, e, lane);
       reprune_select2v<ER, C, S, T>(g, lg, w, e, (uint32_t)lc, (int)cap, old, n_old, R, cnt, lane, keep_add, tmp, a.lcap);   // :568
       ++n_reprunes;
       uint32_t n_keep, n_add, n_rem;                              // update_node_connections (core.rs:776-822)
       reprune_delta<ER>(R, old, n_old, keep_add, rem, n_keep, n_add, n_rem, lane);
-      view_store(g, lg, e, (uint32_t)lc, keep_add, n_keep + n_add, lane);
+      view_store(g, lg, e, (uint32_t)lc, keep_add, n_keep + n_add, n_old, lane);
       for (uint32_t t = 0; t < n_add; ++t) {                      // :793-796 (no cap check on the other side)
         const uint32_t x = keep_add[n_keep + t];
         uint32_t len = view_load(g, lg, x, (uint32_t)lc, edit, a.lcap, lane);
@@ -328,8 +550,8 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
         }
         if (list_find(edit, len, e, lane) < 0) {
           if (lane == 0) edit[len] = e;
-          ++len;
-          view_store(g, lg, x, (uint32_t)lc, edit, len, lane);
+          lg.op(row_key(g, x, (uint32_t)lc), e, lane);
+          view_store(g, lg, x, (uint32_t)lc, edit, len + 1, len, lane);
         }
       }
       for (uint32_t t = 0; t < n_rem; ++t) {                      // :805-816
@@ -339,7 +561,8 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
         const int p = list_find(edit, len, e, lane);
         if (p < 0) continue;
         list_erase(edit, len, p, lane);
-        view_store(g, lg, x, (uint32_t)lc, edit, len - 1, lane);
+        lg.op(row_key(g, x, (uint32_t)lc), e | 0x80000000u, lane);
+        view_store(g, lg, x, (uint32_t)lc, edit, len - 1, len, lane);
       }
     }
   }
@@ -353,6 +576,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     hdr[kSpecReads] = lg.n_reads;
     hdr[kSpecEntries] = lg.n_entries;
     hdr[kSpecFlags] = lg.flags;
+    hdr[kSpecOps] = lg.n_ops;
     hdr[kSpecDist] = cnt.n_dist;
     hdr[kSpecReprunes] = n_reprunes;
     uint64_t t_out;
@@ -371,9 +595,11 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
 #ifdef HNSW_PLAIN_BUILD_KERNELS  // no distance arithmetic: defined once, in build_host.cu
 namespace hnsw {
 
-// One CTA commits the longest valid prefix of the window, in stream order.
+// One CTA commits the longest valid prefix of the window, in stream order.  Dynamic shared memory: `lcap` words per warp.
 __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
+  extern __shared__ uint32_t s_bufs[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
+  uint32_t* buf = s_bufs + (size_t)warp * a.lcap;
   __shared__ uint32_t s_need;
   uint32_t committed = 0, reason = 0, dist = 0, reprunes = 0;
   for (uint32_t q = a.frontier; q < a.frontier + a.count; ++q) {
@@ -381,6 +607,7 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
     uint32_t* hdr = a.hdr + (size_t)slot * kSpecHdrWords;
     const uint32_t state = __ldcg(hdr + kSpecState), node = __ldcg(hdr + kSpecNode), snap = __ldcg(hdr + kSpecSnap);
     const uint32_t n_reads = __ldcg(hdr + kSpecReads), n_entries = __ldcg(hdr + kSpecEntries), flags = __ldcg(hdr + kSpecFlags);
+    const uint32_t n_ops = __ldcg(hdr + kSpecOps);
     if (state != 1u || node != q) {
       reason = 1;
       break;
@@ -389,10 +616,25 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
       reason = 2;
       break;
     }
-    // valid iff no row the insert looked at was written after its snapshot
-    const uint32_t* rd = a.rd + (size_t)slot * a.rcap;
+    const uint32_t* wkey = a.wkey + (size_t)slot * a.wmaxe;
+    const uint32_t* woff = a.woff + (size_t)slot * a.wmaxe;
+    const uint32_t* wdata = a.wdata + (size_t)slot * a.wcap;
+    // valid iff nothing the insert depended on was written after its snapshot (the warps share the read records)
     int bad = ((flags & kSpecRdOverflow) && snap != q) ? 1 : 0;
-    for (uint32_t i = tid; i < n_reads; i += blockDim.x) bad |= spec_ver(a, __ldcg(rd + i)) > snap ? 1 : 0;
+    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, n_reads, (uint32_t)warp * 32, (uint32_t)warps * 32, buf, lane) ? 1 : 0;
+    // overflow rows the commit can allocate at most (chains already in place are not counted: an upper bound; a row that
+    // takes operations instead of content grows by a few ids over what it holds)
+    uint32_t need = 0;
+    for (uint32_t e = tid; e < n_entries; e += blockDim.x) {
+      const uint32_t key = __ldcg(wkey + e);
+      if (key == kEmpty) continue;
+      const uint32_t len = __ldcg(wdata + __ldcg(woff + e) + 1);
+      if (len > g.W) need += (len - g.W + kPoolIds - 1) / kPoolIds;
+      if (spec_ver(a, key) > snap) {
+        need += 2;
+        if (flags & kSpecOpOverflow) bad = 1;                     // the operations of this row may be missing
+      }
+    }
     if (tid == 0) s_need = 0;
     bad = __syncthreads_or(bad);
     if (bad) {
@@ -403,27 +645,18 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
       reason = 3;
       break;
     }
-    const uint32_t* wkey = a.wkey + (size_t)slot * a.wmaxe;
-    const uint32_t* woff = a.woff + (size_t)slot * a.wmaxe;
-    const uint32_t* wdata = a.wdata + (size_t)slot * a.wcap;
-    // overflow rows the copy can allocate at most (chains already in place are not counted: an upper bound)
-    uint32_t need = 0;
-    for (uint32_t e = tid; e < n_entries; e += blockDim.x)
-      if (__ldcg(wkey + e) != kEmpty) {
-        const uint32_t len = __ldcg(wdata + __ldcg(woff + e) + 1);
-        if (len > g.W) need += (len - g.W + kPoolIds - 1) / kPoolIds;
-      }
     if (need) atomicAdd(&s_need, need);
     __syncthreads();
     if ((uint32_t)__ldcg(g.meta + kMetaPoolUsed) + s_need > g.pool_cap) {
       reason = 4;
       break;
     }
+    const uint32_t* okey = a.okey + (size_t)slot * a.ocap;
+    const uint32_t* oval = a.oval + (size_t)slot * a.ocap;
     for (uint32_t e = warp; e < n_entries; e += warps) {
       const uint32_t key = __ldcg(wkey + e);
       if (key == kEmpty) continue;
       const uint32_t* p = wdata + __ldcg(woff + e);
-      const uint32_t len = __ldcg(p + 1);
       uint32_t *row, *ovf;
       if (key & 0x80000000u) {
         const uint32_t r = key & 0x7FFFFFFFu;
@@ -431,7 +664,38 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
       } else {
         row = g.adj0 + (size_t)key * g.W, ovf = g.ovf0 + key;
       }
-      list_store(g, row, ovf, p + 2, len, lane);
+      if (spec_ver(a, key) <= snap) {
+        list_store(g, row, ovf, p + 2, __ldcg(p + 1), lane);      // the row the insert saw is the row that is there
+      } else {
+        // written since the snapshot by inserts this one did not depend on: its appends / removals apply to what the row
+        // holds now (add_neighbor / remove_neighbor, core.rs:137-152), in program order
+        __syncwarp();
+        uint32_t len = list_load(g, row, ovf, buf, a.lcap, lane);
+        bool ok = len != kEmpty;
+        for (uint32_t i = 0; i < n_ops && ok; i += 32) {
+          uint32_t mask = __ballot_sync(kFull, i + lane < n_ops && __ldcg(okey + i + lane) == key);
+          while (mask && ok) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t v = __ldcg(oval + i + b), id = v & 0x7FFFFFFFu;
+            const int pos = list_find(buf, len, id, lane);
+            if (v & 0x80000000u) {
+              if (pos >= 0) list_erase(buf, len, pos, lane), --len;
+            } else if (pos < 0) {
+              if (len + 1 > a.lcap) {
+                ok = false;
+              } else {
+                if (lane == 0) buf[len] = id;
+                ++len;
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (ok) list_store(g, row, ovf, buf, len, lane);
+        else if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
+        if (lane == 0) atomicAdd(a.ctl + kSpecOpRows, 1u);
+      }
       if (lane == 0) {
         if (key & 0x80000000u) a.verU[key & 0x7FFFFFFFu] = q + 1;
         else a.ver0[key] = q + 1;

@@ -131,7 +131,7 @@ class DeviceIndex:
         n = C.c_uint32()
         _check(self._L.hnsw_index_build_stats_ex(self._h, _p(ex, C.c_uint64), ex.size, C.byref(n)))
         names = ("fast_worklist_dropped", "fast_reprunes_skipped", "fast_edges_refused", "spec_rounds", "spec_executions",
-                 "spec_dist_evals_wasted", "spec_exact_fallbacks", "spec_max_window")
+                 "spec_dist_evals_wasted", "spec_exact_fallbacks", "spec_max_window", "spec_rows_as_operations")
         d.update({k: int(ex[4 + i]) for i, k in enumerate(names)})
         return d
 

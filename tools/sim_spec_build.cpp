@@ -179,9 +179,15 @@ static void insert(uint32_t q) {
     remember(q, lc);
     NB[q][lc] = sel;
     log_write(q, lc, sel);
-    for (uint32_t r : sel) log_strict(r, lc, 5), add_nb(r, lc, q);   // 5: append with a cap check after it (core.rs:561)
-    for (uint32_t e : sel)
-      if ((int)NB[e][lc].size() > cap) reprune(e, lc, cap);
+    for (uint32_t r : sel) add_nb(r, lc, q);                          // an operation on r, whatever r holds
+    for (uint32_t e : sel) {
+      if ((int)NB[e][lc].size() > cap) {
+        reprune(e, lc, cap);
+      } else if (LOG) {                                               // 6: the cap check (core.rs:561) said "fits": the row may
+        const size_t base = OLD && OLD->count(key(e, lc)) ? (*OLD)[key(e, lc)].size() : 0;   // grow by `thr` ids before it says otherwise
+        LOG->reads.push_back({key(e, lc), 6, (uint32_t)base, (float)(cap - (int)NB[e][lc].size())});
+      }
+    }
   }
   if (l > l_max) max_layer = l, entry = q;
 }
@@ -222,7 +228,7 @@ static int verify(size_t n, const std::vector<size_t>& cps, int B) {
   for (size_t cp : cps) {
     for (; next < cp && next < n; ++next) insert((uint32_t)next);
     size_t accepted[3] = {0, 0, 0}, violations[3] = {0, 0, 0}, total = 0, prefix_sum[3] = {0, 0, 0};
-    const int windows = 12;
+    const int windows = getenv("SIM_WINDOWS") ? atoi(getenv("SIM_WINDOWS")) : 12;
     for (int wdx = 0; wdx < windows && next + B < n; ++wdx) {
       NB_snap = NB_true;
       std::vector<Run> truth;
@@ -268,12 +274,9 @@ static int verify(size_t n, const std::vector<size_t>& cps, int B) {
               op_hit = fine_hit;
             } else if (rd.kind == 3 || rd.kind == 4) {
               op_hit = false;                       // append / remove of one id on a row others only appended to or removed from
-            } else if (rd.kind == 5) {              // append followed by the cap check: the decision must not change
-              const int lvl = (int)(rd.row >> 32);
-              const size_t cap = lvl == 0 ? 2 * M : M;
-              const size_t snap_len = NB_snap[(uint32_t)rd.row][lvl].size();   // (restored by the undo)
-              const size_t true_len = tru.before.count(rd.row) ? tru.before[rd.row].size() : snap_len;
-              op_hit = (snap_len + 1 > cap) != (true_len + 1 > cap);
+            } else if (rd.kind == 6) {              // the cap check must still say "fits" on the row as it really is
+              const size_t true_len = tru.before.count(rd.row) ? tru.before[rd.row].size() : after.size();
+              op_hit = true_len > (size_t)rd.qnode + (size_t)rd.thr;
               (void)n_added;
             }
             if (fine_hit) conflict[1] = true;
@@ -327,6 +330,116 @@ static int verify(size_t n, const std::vector<size_t>& cps, int B) {
   return 0;
 }
 
+// ---------------------------------------------------------------- pipe mode: in-order commit WITHOUT rounds
+// SIM_PIPE=1: event simulation of W persistent warps.  A warp takes the next insert, executes it against the graph as it
+// stands (snapshot = commit frontier at that moment, T = 0.9 ms x reads / 355), waits until it is the oldest, validates,
+// commits (c = 15 us) or re-executes.  early = re-execute as soon as a commit invalidates a finished execution instead
+// of waiting to become the head.  Reports inserts/s for coarse and fine+op-log validation.
+static bool run_conflicts(const Run& spec, const Run& tru, int crit) {
+  for (const Read& rd : spec.log.reads) {
+    auto bj = tru.before.find(rd.row);
+    if (bj == tru.before.end()) continue;
+    const auto& before = bj->second;
+    const auto& after = tru.after.at(rd.row);
+    std::vector<uint32_t> changed;
+    for (uint32_t x : after) if (std::find(before.begin(), before.end(), x) == before.end()) changed.push_back(x);
+    for (uint32_t x : before) if (std::find(after.begin(), after.end(), x) == after.end()) changed.push_back(x);
+    if (changed.empty()) continue;
+    if (crit == 0) return true;
+    if (rd.kind == 1 || rd.kind == 2) {
+      if (rd.thr == -INFINITY) return true;
+      for (uint32_t x : changed) {
+        if (x == rd.qnode) continue;
+        const float sv = sim(rd.qnode, x);
+        if (rd.kind == 1 ? sv > rd.thr : sv >= rd.thr) return true;
+      }
+    } else if (rd.kind == 3 || rd.kind == 4) {
+      continue;
+    } else if (rd.kind == 6) {
+      if (after.size() > (size_t)rd.qnode + (size_t)rd.thr) return true;
+    } else {
+      return true;
+    }
+  }
+  return false;
+}
+
+struct Flight {
+  uint32_t q, snap;
+  double finish;
+  bool finished, invalid;
+  Run spec;
+};
+
+static int pipe_sim(size_t n, const std::vector<size_t>& cps) {
+  stamp.assign(n, 0);
+  NB[0].resize(1);
+  size_t next = 1;
+  const double Tbase = 0.9e-3, c_commit = 15e-6;
+  const int per_cfg = getenv("SIM_PIPE_N") ? atoi(getenv("SIM_PIPE_N")) : 1500;
+  for (size_t cp : cps) {
+    for (; next < cp && next < n; ++next) insert((uint32_t)next);
+    for (int crit : {0, 2})
+      for (int early : {0, 1})
+        for (int W : {8, 16, 32, 64, 128}) {
+          if (next + per_cfg + 200 >= n) return 0;
+          const size_t first = next, last = next + per_cfg;
+          std::vector<Flight*> fl;          // in flight, ordered by q
+          double now = 0;
+          uint64_t execs = 0;
+          auto start = [&](Flight* f) {
+            f->spec = Run();
+            f->snap = (uint32_t)next;       // the commit frontier
+            run_insert(f->q, &NB_true, f->spec, true);
+            f->finish = now + Tbase * (double)f->spec.log.reads.size() / 355.0;
+            f->finished = false, f->invalid = false;
+            ++execs;
+          };
+          size_t ticket = next;
+          while (next < last) {
+            while ((int)fl.size() < W && ticket < last) {   // free warps take tickets
+              Flight* f = new Flight();
+              f->q = (uint32_t)ticket++;
+              fl.push_back(f);
+              start(f);
+            }
+            // next event: the earliest finish of a running execution, or the head's commit if it is ready
+            Flight* head = fl.front();
+            if (head->finished && !head->invalid) {
+              now += c_commit;
+              Run tru;
+              const bool raises = LEVEL[head->q] > max_layer;
+              run_insert(head->q, &NB_true, tru, false);
+              ++next;
+              fl.erase(fl.begin());
+              for (Flight* f : fl)
+                if (!f->invalid && (raises || run_conflicts(f->spec, tru, crit))) {
+                  f->invalid = true;
+                  if (f->finished && early) start(f);
+                }
+              delete head;
+              continue;
+            }
+            if (head->finished && head->invalid) {   // (only without early re-execution)
+              start(head);
+              continue;
+            }
+            Flight* e = nullptr;
+            for (Flight* f : fl)
+              if (!f->finished && (!e || f->finish < e->finish)) e = f;
+            now = std::max(now, e->finish);
+            e->finished = true;
+            if (e->invalid) start(e);                // validation at the end of the execution: stale, run again
+          }
+          for (Flight* f : fl) delete f;   // (none: the loop ends when everything is committed)
+          printf("N=%zu %s early=%d W=%3d : %7.0f inserts/s  executions/insert %.2f\n", first, crit ? "fine+oplog" : "coarse    ", early, W,
+                 (double)(last - first) / now, (double)execs / (double)(last - first));
+          fflush(stdout);
+        }
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 8) return 1;
   const char* path = argv[1];
@@ -349,6 +462,7 @@ int main(int argc, char** argv) {
   }
   LEVEL[0] = 0;
   NB.resize(n);
+  if (getenv("SIM_PIPE")) return pipe_sim(n, cps);
   if (getenv("SIM_VERIFY")) return verify(n, cps, atoi(getenv("SIM_VERIFY")));
   stamp.assign(n, 0);
   NB[0].resize(1);
