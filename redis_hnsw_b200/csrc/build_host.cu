@@ -475,9 +475,10 @@ int Index::add_spec(uint32_t first, uint32_t count) {
                o_rdo = o_rdh + al((size_t)ring * rmax * 16), o_rd = o_rdo + al((size_t)ring * rmax * 4),
                o_okey = o_rd + al((size_t)ring * rcap * 4), o_oval = o_okey + al((size_t)ring * ocap * 4),
                o_wkey = o_oval + al((size_t)ring * ocap * 4), o_woff = o_wkey + al((size_t)ring * wmaxe * 4),
-               o_wdata = o_woff + al((size_t)ring * wmaxe * 4), total = o_wdata + al((size_t)ring * wcap * 4);
+               o_wbase = o_woff + al((size_t)ring * wmaxe * 4), o_wdata = o_wbase + al((size_t)ring * wmaxe * 4),
+               total = o_wdata + al((size_t)ring * wcap * 4);
   // K2: one list buffer per warp
-  const int k2_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / ((size_t)lcap * 4)));
+  const int k2_warps = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(200 * 1024) / ((size_t)lcap * 4)));
   const size_t k2_smem = (size_t)k2_warps * lcap * 4;
   if (k2_smem > 48 * 1024) cudaFuncSetAttribute(spec_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem);
   int rc = ensure_scratch(s_spec, total);
@@ -498,6 +499,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   a.oval = (uint32_t*)(base + o_oval);
   a.wkey = (uint32_t*)(base + o_wkey);
   a.woff = (uint32_t*)(base + o_woff);
+  a.wbase = (uint32_t*)(base + o_wbase);
   a.wdata = (uint32_t*)(base + o_wdata);
 
   uint32_t f = first;
@@ -515,11 +517,14 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     const double t_round = trace ? now_ms() : 0;
     uint32_t B = opt_spec_window ? opt_spec_window : (uint32_t)std::max(8.0, 0.1 * (opt_spec_mult ? opt_spec_mult : 30) * ema);
     B = std::min(std::min(B, resident), end - f);
-    // a node that raises max_layer becomes the enterpoint of everything after it (core.rs:587-593): the window ends there
-    uint32_t wend = f + B;
-    for (uint32_t q = f; q < wend; ++q)
+    // a node that raises max_layer becomes the enterpoint of everything after it (core.rs:587-593): the window ends there,
+    // and so does the stretch behind the window in which nodes with upper levels prepare (K1: checkpoints)
+    const uint32_t ahead = opt_spec_ahead < 0 ? 0 : (opt_spec_ahead ? (uint32_t)opt_spec_ahead : 2 * B);
+    uint32_t wend = f + B, pend = (uint32_t)std::min<uint64_t>((uint64_t)f + B + ahead, std::min<uint64_t>(end, (uint64_t)f + ring));
+    for (uint32_t q = f; q < pend; ++q)
       if (h_level[q] > max_layer) {
-        wend = q + 1;
+        wend = std::min(wend, q + 1);
+        pend = q + 1;
         break;
       }
     B = wend - f;
@@ -528,7 +533,7 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     a.count = B;
     a.ver0 = d_ver0;
     a.verU = d_verU;
-    LaunchCfg c1{(int)B, 32, smem, stream};
+    LaunchCfg c1{(int)(pend - f), 32, smem, stream};
     g_launches++;
     if (trace) cudaEventRecord(ev[0], stream);
     e = run_spec(kind, efr, small, c1, g, a, false, nullptr);
@@ -579,6 +584,8 @@ int Index::add_spec(uint32_t first, uint32_t count) {
           const uint32_t* w = &hh[(size_t)((a.frontier + i) & (ring - 1)) * kSpecHdrWords];
           std::fprintf(stderr, " %u:%u,%.0f,%.0f%s", i, w[kSpecSm] & 0xFFFFu, (w[kSpecT0] - t_min) / 1e3, w[kSpecDur] / 1e3,
                        (w[kSpecSm] & 0x80000000u) ? "x" : "");
+          if (w[kSpecSm] & 0x80000000u)   // executed: level, ns in searches, ns in re-selections, re-selections
+            std::fprintf(stderr, "[L%d s%.0f r%.0f n%u]", h_level[a.frontier + i], w[kSpecTSearch] / 1e3, w[kSpecTSelect] / 1e3, w[kSpecReprunes]);
         }
         std::fprintf(stderr, "\n");
       }

@@ -42,8 +42,8 @@ namespace hnsw {
 static_assert(!kLookaheadInBuilders, "search_layer2_la does not report row ids to the search hook: the SPEC read log needs them");
 
 enum SpecHdr : int {
-  kSpecState = 0,     // 0 = needs execution, 1 = executed (logs valid for `snap`)
-  kSpecSnap = 1,      // every insert with id < snap was committed when the logs were made
+  kSpecState = 0,     // 0 = needs execution, 1 = executed, 2 = only the levels above 0 are done (checkpoint, see K1)
+  kSpecSnap = 1,      // every insert with id < snap was committed when the level-0 part of the logs was made
   kSpecNode = 2,
   kSpecReads = 3,
   kSpecEntries = 4,
@@ -54,7 +54,18 @@ enum SpecHdr : int {
   kSpecDur = 9,       //              ns it spent there,
   kSpecSm = 10,       //              SM it ran on | 0x80000000 when it executed (not just validated)
   kSpecOps = 11,      // operations logged (fine validation)
-  kSpecHdrWords = 12,
+  kSpecSnapU = 12,    // the same snapshot id for the part above level 0 (rows with bit 31 set in their key)
+  kSpecCpReads = 13,  // checkpoint = the logs and counters as they stood when level 0 began: read records,
+  kSpecCpRused = 14,  //   id words behind them,
+  kSpecCpEntries = 15,  // write-log entries,
+  kSpecCpUsed = 16,   //   words behind them,
+  kSpecCpOps = 17,    //   operations,
+  kSpecCpEp = 18,     //   entry point of the level-0 search,
+  kSpecCpDist = 19,
+  kSpecCpReprunes = 20,
+  kSpecTSearch = 21,  // diagnostics: ns of this execution inside search_level,
+  kSpecTSelect = 22,  //              ns inside the re-selections (sweep + top-m)
+  kSpecHdrWords = 24,
 };
 constexpr uint32_t kSpecRdOverflow = 1, kSpecWrOverflow = 2, kSpecOpOverflow = 4;
 // read kinds (word y of a read record = kind | len << 3)
@@ -72,12 +83,13 @@ enum SpecCtl : int {
   kSpecEntry = 8,
   kSpecError = 9,
   kSpecOpRows = 10,    // rows committed as operations on newer content (accumulates)
+  kSpecPrepared = 11,  // checkpoints made behind the window (accumulates)
   kSpecCtlWords = 16,
 };
 
 struct SpecArgs {
   uint32_t frontier;   // first insert of the window; every id below is committed
-  uint32_t count;      // window size
+  uint32_t count;      // window size (K1 may be launched with more blocks: nodes behind the window only prepare, see K1)
   uint32_t ring;       // slots (power of two); slot = id & (ring - 1)
   uint32_t m, cap0, capU, efc, lcap, vis_slots;
   uint32_t rcap, wcap, wmaxe;
@@ -91,6 +103,7 @@ struct SpecArgs {
   uint32_t* oval;      // [ring][ocap]   id to append, or id | 0x80000000 to remove
   uint32_t* wkey;      // [ring][wmaxe]  row key of entry e (kEmpty = dead)
   uint32_t* woff;      // [ring][wmaxe]  word offset of entry e in wdata: {reserved, len, ids...}
+  uint32_t* wbase;     // [ring][wmaxe]  length of the graph's row when entry e was made
   uint32_t* wdata;     // [ring][wcap]
   uint32_t* ver0;      // [n]   1 + id of the last insert that wrote the level-0 row
   uint32_t* verU;      // [nU]
@@ -321,6 +334,12 @@ __device__ __forceinline__ void reprune_select2v(const Graph& g, SpecLog& lg, Wa
   if (lg.fine) lg.patch_thr(first_sweep, L.worst, lane);         // -inf while fewer than `cap` candidates exist
 }
 
+__device__ __forceinline__ uint64_t spec_now() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------- validation (K1 for kept logs, K2 before a commit)
 
 // sim of two slab rows, any summation order: only ever compared with a margin (spec_read_conflicts)
@@ -386,20 +405,26 @@ __device__ __forceinline__ bool spec_read_conflicts(const Graph& g, const SpecAr
   return hit;
 }
 
-// One warp walks the read records [first, n_reads) of a slot with stride `step`; true (warp-uniform) = a dependency was lost.
-__device__ __forceinline__ bool spec_reads_conflict(const Graph& g, const SpecArgs& a, uint32_t slot, uint32_t snap, uint32_t n_reads,
-                                                    uint32_t first, uint32_t step, uint32_t* buf, int lane) {
+// rows above level 0 (bit 31 of the key) and level-0 rows may have been read at different snapshots (checkpoint, K1)
+__device__ __forceinline__ uint32_t spec_snap_of(uint32_t key, uint32_t snap0, uint32_t snapU) {
+  return (key & 0x80000000u) ? snapU : snap0;
+}
+
+// One warp walks the read records lo + first, lo + first + step, ... < hi of a slot (32 at a time); true (warp-uniform) =
+// a dependency was lost.
+__device__ __forceinline__ bool spec_reads_conflict(const Graph& g, const SpecArgs& a, uint32_t slot, uint32_t snap0, uint32_t snapU,
+                                                    uint32_t lo, uint32_t hi, uint32_t first, uint32_t step, uint32_t* buf, int lane) {
   const uint4* rdh = a.rdh + (size_t)slot * a.rmax;
   const uint32_t* rdo = a.rdo + (size_t)slot * a.rmax;
   const uint32_t* rd = a.rd + (size_t)slot * a.rcap;
-  for (uint32_t i = first; i < n_reads; i += step) {
+  for (uint32_t i = lo + first; i < hi; i += step) {
     uint4 h = make_uint4(0, 0, 0, 0);
     uint32_t off = 0;
     bool stale = false;
-    if (i + lane < n_reads) {
+    if (i + lane < hi) {
       h = __ldcg(rdh + i + lane);
       off = __ldcg(rdo + i + lane);
-      stale = spec_ver(a, h.x) > snap;
+      stale = spec_ver(a, h.x) > spec_snap_of(h.x, snap0, snapU);
     }
     if (__any_sync(kFull, stale && ((h.y & 7u) == kRdStrict || !a.fine))) return true;
     uint32_t mask = __ballot_sync(kFull, stale);
@@ -445,24 +470,40 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   uint32_t* edit = rem + a.lcap;
   uint32_t* tmp = edit + a.lcap;
 
-  // executed earlier and still valid?  (writes after the snapshot to what the insert depended on void the logs)
-  if (__ldcg(hdr + kSpecState) == 1u && __ldcg(hdr + kSpecNode) == q) {
-    const uint32_t snap = __ldcg(hdr + kSpecSnap), n_reads = __ldcg(hdr + kSpecReads), flags = __ldcg(hdr + kSpecFlags);
+  // Nodes behind the window (blockIdx >= count) that have upper levels only PREPARE: they run the levels above 0 — a second
+  // ef_construction search, as long as the level-0 one — and leave a checkpoint, so that the insert costs one search when
+  // its turn comes.  Rows above level 0 change 16x less often than level-0 rows, so the checkpoint usually survives.
+  const bool far = blockIdx.x >= a.count;
+  const int l = g.level[q];
+  if (far && l == 0) return;
+  const uint32_t state = __ldcg(hdr + kSpecState);
+  bool resume = false;                                            // the part above level 0 is done and still valid
+  uint32_t snapU = a.frontier;
+  if ((state == 1u || state == 2u) && __ldcg(hdr + kSpecNode) == q) {
+    const uint32_t snap0 = __ldcg(hdr + kSpecSnap), flags = __ldcg(hdr + kSpecFlags), cp_reads = __ldcg(hdr + kSpecCpReads);
+    const uint32_t n_reads = __ldcg(hdr + kSpecReads);
+    snapU = __ldcg(hdr + kSpecSnapU);
     if (flags & kSpecWrOverflow) return;                          // unusable either way: the host runs it through EXACT
     // Warp-uniform control flow on purpose: a per-lane early exit from this loop left the warp split into groups that
     // ran the whole insert below one after the other (measured: 4.1 ms instead of 0.9 ms per execution, r2 call D).
-    bool bad = (flags & kSpecRdOverflow) && snap != q;
-    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, n_reads, 0, 32, tmp, lane);
-    if (!bad && (flags & kSpecOpOverflow)) {                      // operations missing: every written row must be untouched
-      const uint32_t n_entries = __ldcg(hdr + kSpecEntries);
-      const uint32_t* wk = a.wkey + (size_t)slot * a.wmaxe;
-      for (uint32_t i = 0; i < n_entries && !bad; i += 32) {
-        const uint32_t key = i + lane < n_entries ? __ldcg(wk + i + lane) : kEmpty;
-        bad = __any_sync(kFull, key != kEmpty && spec_ver(a, key) > snap);
+    // A log that overflowed is only good at the head of a window, where nothing can be stale.
+    const bool whole = !(flags & (kSpecRdOverflow | kSpecOpOverflow)) || (snap0 == q && snapU == q);
+    const bool okU = whole && !spec_reads_conflict(g, a, slot, snap0, snapU, 0, cp_reads, 0, 32, tmp, lane);
+    if (okU && state == 2u) {
+      if (far) return;                                            // prepared, still good
+      resume = true;
+    } else if (okU) {
+      if (!spec_reads_conflict(g, a, slot, snap0, snapU, cp_reads, n_reads, 0, 32, tmp, lane)) return;   // executed, still good
+      if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist] - hdr[kSpecCpDist]);
+      if (far) {                                                  // (a window that shrank): keep the checkpoint
+        if (lane == 0) hdr[kSpecState] = 2u;
+        return;
       }
+      resume = true;
+    } else {
+      if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, state == 1u ? hdr[kSpecDist] : hdr[kSpecCpDist]);
+      snapU = a.frontier;
     }
-    if (!bad) return;
-    if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist]);
     __syncwarp();
   }
 
@@ -480,21 +521,58 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   lg.n_reads = lg.rused = lg.n_entries = lg.used = lg.n_ops = lg.flags = 0;
   lg.cur_open = false;
   SpecSearchHook hook{g.upper_base, &lg, lane};
+  uint32_t* wkey = a.wkey + (size_t)slot * a.wmaxe;
+  uint32_t* woff = a.woff + (size_t)slot * a.wmaxe;
+  uint32_t* wbase = a.wbase + (size_t)slot * a.wmaxe;
 
   CandList<EFR> L;
   CandList<ER> R;
   Counters cnt = {0, 0, 0};
-  uint32_t n_reprunes = 0;
+  uint32_t n_reprunes = 0, t_search = 0, t_select = 0;
 
-  const int l = g.level[q];
-  const int l_max = g.meta[kMetaMaxLayer];                        // core.rs:496
+  int lc_first = g.meta[kMetaMaxLayer];                           // core.rs:496
   uint32_t ep = (uint32_t)g.meta[kMetaEntry];                     // core.rs:508
-  for (int lc = l_max; lc >= 0; --lc) {
+  uint32_t cp_reads = 0, cp_rused = 0, cp_entries = 0, cp_used = 0, cp_ops = 0, cp_ep = ep, cp_dist = 0, cp_reprunes = 0;
+  if (resume) {                                                   // back to the checkpoint: logs truncated, level 0 to do
+    cp_reads = __ldcg(hdr + kSpecCpReads), cp_rused = __ldcg(hdr + kSpecCpRused), cp_entries = __ldcg(hdr + kSpecCpEntries);
+    cp_used = __ldcg(hdr + kSpecCpUsed), cp_ops = __ldcg(hdr + kSpecCpOps), cp_ep = __ldcg(hdr + kSpecCpEp);
+    cp_dist = __ldcg(hdr + kSpecCpDist), cp_reprunes = __ldcg(hdr + kSpecCpReprunes);
+    lg.n_reads = cp_reads, lg.rused = cp_rused, lg.n_entries = cp_entries, lg.used = cp_used, lg.n_ops = cp_ops;
+    for (uint32_t i = lane; i < cp_entries; i += 32)
+      lg.wkey_s[i] = __ldcg(wkey + i), lg.woff_s[i] = __ldcg(woff + i), lg.wbase_s[i] = __ldcg(wbase + i);
+    __syncwarp();
+    ep = cp_ep, cnt.n_dist = cp_dist, n_reprunes = cp_reprunes;
+    lc_first = 0;
+  }
+  for (int lc = lc_first; lc >= 0; --lc) {
+    if (lc == 0 && !resume) {                                     // checkpoint: everything above level 0 is done
+      cp_reads = lg.n_reads, cp_rused = lg.rused, cp_entries = lg.n_entries, cp_used = lg.used, cp_ops = lg.n_ops;
+      cp_ep = ep, cp_dist = cnt.n_dist, cp_reprunes = n_reprunes;
+      if (far && !lg.flags) {
+        __syncwarp();
+        for (uint32_t i = lane; i < lg.n_entries; i += 32) wkey[i] = lg.wkey_s[i], woff[i] = lg.woff_s[i], wbase[i] = lg.wbase_s[i];
+        if (lane == 0) {
+          hdr[kSpecNode] = q, hdr[kSpecSnapU] = snapU, hdr[kSpecFlags] = 0;
+          hdr[kSpecCpReads] = cp_reads, hdr[kSpecCpRused] = cp_rused, hdr[kSpecCpEntries] = cp_entries, hdr[kSpecCpUsed] = cp_used;
+          hdr[kSpecCpOps] = cp_ops, hdr[kSpecCpEp] = cp_ep, hdr[kSpecCpDist] = cp_dist, hdr[kSpecCpReprunes] = cp_reprunes;
+          uint64_t t_out;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_out));
+          hdr[kSpecDur] = (uint32_t)(t_out - t_in);
+          hdr[kSpecSm] = smid | 0x40000000u;
+          __threadfence();
+          hdr[kSpecState] = 2u;
+          atomicAdd(a.ctl + kSpecPrepared, 1u);
+        }
+        return;
+      }
+    }
     const bool link = lc <= l;
     const uint32_t cap = lc == 0 ? a.cap0 : a.capU;               // core.rs:560
     load_q_from_slab<C, S, T>(w, g, q, lane);
+    const uint64_t t_s0 = spec_now();
     if constexpr (kLookahead) search_layer2_la<EFR, C, S, T>(g, w, lb, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane, hook);   // :513, :524
     else search_layer2<EFR, C, S, T, RowCopy<C>::kDefault>(g, w, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane, hook);
+    t_search += (uint32_t)(spec_now() - t_s0);
     float s;
     L.get(0, lane, false, ep, s);                                 // :514 / :576
     if (!link) continue;
@@ -536,7 +614,9 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
       }
       if (lg.fine) lg.read_plain(row_key(g, e, (uint32_t)lc), kRdStrict, 0, 0, lane);   // re-selected: its content decides
       load_q_from_slab<C, S, T>(w, g, e, lane);
+      const uint64_t t_r0 = spec_now();
       reprune_select2v<ER, C, S, T>(g, lg, w, e, (uint32_t)lc, (int)cap, old, n_old, R, cnt, lane, keep_add, tmp, a.lcap);   // :568
+      t_select += (uint32_t)(spec_now() - t_r0);
       ++n_reprunes;
       uint32_t n_keep, n_add, n_rem;                              // update_node_connections (core.rs:776-822)
       reprune_delta<ER>(R, old, n_old, keep_add, rem, n_keep, n_add, n_rem, lane);
@@ -567,12 +647,13 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     }
   }
   __syncwarp();
-  uint32_t* wkey = a.wkey + (size_t)slot * a.wmaxe;
-  uint32_t* woff = a.woff + (size_t)slot * a.wmaxe;
-  for (uint32_t i = lane; i < lg.n_entries; i += 32) wkey[i] = lg.wkey_s[i], woff[i] = lg.woff_s[i];
+  for (uint32_t i = lane; i < lg.n_entries; i += 32) wkey[i] = lg.wkey_s[i], woff[i] = lg.woff_s[i], wbase[i] = lg.wbase_s[i];
   if (lane == 0) {
     hdr[kSpecSnap] = a.frontier;
+    hdr[kSpecSnapU] = snapU;
     hdr[kSpecNode] = q;
+    hdr[kSpecCpReads] = cp_reads, hdr[kSpecCpRused] = cp_rused, hdr[kSpecCpEntries] = cp_entries, hdr[kSpecCpUsed] = cp_used;
+    hdr[kSpecCpOps] = cp_ops, hdr[kSpecCpEp] = cp_ep, hdr[kSpecCpDist] = cp_dist, hdr[kSpecCpReprunes] = cp_reprunes;
     hdr[kSpecReads] = lg.n_reads;
     hdr[kSpecEntries] = lg.n_entries;
     hdr[kSpecFlags] = lg.flags;
@@ -583,6 +664,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_out));
     hdr[kSpecDur] = (uint32_t)(t_out - t_in);
     hdr[kSpecSm] = smid | 0x80000000u;
+    hdr[kSpecTSearch] = t_search, hdr[kSpecTSelect] = t_select;
     __threadfence();
     hdr[kSpecState] = 1u;
     atomicAdd(a.ctl + kSpecExecuted, 1u);
@@ -596,7 +678,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
 namespace hnsw {
 
 // One CTA commits the longest valid prefix of the window, in stream order.  Dynamic shared memory: `lcap` words per warp.
-__global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
+__global__ void __launch_bounds__(512) spec_commit_kernel(Graph g, SpecArgs a) {
   extern __shared__ uint32_t s_bufs[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
   uint32_t* buf = s_bufs + (size_t)warp * a.lcap;
@@ -607,7 +689,7 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
     uint32_t* hdr = a.hdr + (size_t)slot * kSpecHdrWords;
     const uint32_t state = __ldcg(hdr + kSpecState), node = __ldcg(hdr + kSpecNode), snap = __ldcg(hdr + kSpecSnap);
     const uint32_t n_reads = __ldcg(hdr + kSpecReads), n_entries = __ldcg(hdr + kSpecEntries), flags = __ldcg(hdr + kSpecFlags);
-    const uint32_t n_ops = __ldcg(hdr + kSpecOps);
+    const uint32_t n_ops = __ldcg(hdr + kSpecOps), snapU = __ldcg(hdr + kSpecSnapU);
     if (state != 1u || node != q) {
       reason = 1;
       break;
@@ -620,8 +702,9 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
     const uint32_t* woff = a.woff + (size_t)slot * a.wmaxe;
     const uint32_t* wdata = a.wdata + (size_t)slot * a.wcap;
     // valid iff nothing the insert depended on was written after its snapshot (the warps share the read records)
-    int bad = ((flags & kSpecRdOverflow) && snap != q) ? 1 : 0;
-    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, n_reads, (uint32_t)warp * 32, (uint32_t)warps * 32, buf, lane) ? 1 : 0;
+    // (a log that overflowed is only good at the head of a window, where nothing can be stale)
+    int bad = ((flags & (kSpecRdOverflow | kSpecOpOverflow)) && !(snap == q && snapU == q)) ? 1 : 0;
+    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, snapU, 0, n_reads, (uint32_t)warp * 32, (uint32_t)warps * 32, buf, lane) ? 1 : 0;
     // overflow rows the commit can allocate at most (chains already in place are not counted: an upper bound; a row that
     // takes operations instead of content grows by a few ids over what it holds)
     uint32_t need = 0;
@@ -630,10 +713,7 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
       if (key == kEmpty) continue;
       const uint32_t len = __ldcg(wdata + __ldcg(woff + e) + 1);
       if (len > g.W) need += (len - g.W + kPoolIds - 1) / kPoolIds;
-      if (spec_ver(a, key) > snap) {
-        need += 2;
-        if (flags & kSpecOpOverflow) bad = 1;                     // the operations of this row may be missing
-      }
+      if (spec_ver(a, key) > spec_snap_of(key, snap, snapU)) need += 2;
     }
     if (tid == 0) s_need = 0;
     bad = __syncthreads_or(bad);
@@ -664,7 +744,7 @@ __global__ void __launch_bounds__(256) spec_commit_kernel(Graph g, SpecArgs a) {
       } else {
         row = g.adj0 + (size_t)key * g.W, ovf = g.ovf0 + key;
       }
-      if (spec_ver(a, key) <= snap) {
+      if (spec_ver(a, key) <= spec_snap_of(key, snap, snapU)) {
         list_store(g, row, ovf, p + 2, __ldcg(p + 1), lane);      // the row the insert saw is the row that is there
       } else {
         // written since the snapshot by inserts this one did not depend on: its appends / removals apply to what the row
