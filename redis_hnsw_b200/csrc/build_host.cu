@@ -475,8 +475,8 @@ int Index::add_spec(uint32_t first, uint32_t count) {
                o_rdo = o_rdh + al((size_t)ring * rmax * 16), o_rd = o_rdo + al((size_t)ring * rmax * 4),
                o_okey = o_rd + al((size_t)ring * rcap * 4), o_oval = o_okey + al((size_t)ring * ocap * 4),
                o_wkey = o_oval + al((size_t)ring * ocap * 4), o_woff = o_wkey + al((size_t)ring * wmaxe * 4),
-               o_wbase = o_woff + al((size_t)ring * wmaxe * 4), o_wdata = o_wbase + al((size_t)ring * wmaxe * 4),
-               total = o_wdata + al((size_t)ring * wcap * 4);
+               o_wbase = o_woff + al((size_t)ring * wmaxe * 4), o_ssel = o_wbase + al((size_t)ring * wmaxe * 4),
+               o_wdata = o_ssel + al((size_t)ring * ((m + 31) & ~31u) * 4), total = o_wdata + al((size_t)ring * wcap * 4);
   // K2: one list buffer per warp
   const int k2_warps = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(200 * 1024) / ((size_t)lcap * 4)));
   const size_t k2_smem = (size_t)k2_warps * lcap * 4;
@@ -500,13 +500,15 @@ int Index::add_spec(uint32_t first, uint32_t count) {
   a.wkey = (uint32_t*)(base + o_wkey);
   a.woff = (uint32_t*)(base + o_woff);
   a.wbase = (uint32_t*)(base + o_wbase);
+  a.ssel = (uint32_t*)(base + o_ssel);
+  a.budget_ns = opt_spec_budget_us > 0 ? (uint32_t)opt_spec_budget_us * 1000u : 0u;
   a.wdata = (uint32_t*)(base + o_wdata);
 
   uint32_t f = first;
   const uint32_t end = first + count;
   double ema = 4.0;  // committed inserts per round
   uint32_t h[kSpecCtlWords];
-  uint32_t prev_exec = 0, prev_dist = 0, prev_repr = 0, prev_waste = 0, prev_oprows = 0;
+  uint32_t prev_exec = 0, prev_dist = 0, prev_repr = 0, prev_waste = 0, prev_oprows = 0, idle_rounds = 0;
   const bool trace = std::getenv("HNSW_BUILD_TRACE") != nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double k1_ms = 0, k2_ms = 0, host_ms = 0;
@@ -612,8 +614,10 @@ int Index::add_spec(uint32_t first, uint32_t count) {
     } else if (reason == 4) {
       if ((rc = ensure_pool((uint64_t)g.pool_cap * 2))) return rc;
     } else if (committed == 0) {
-      return fail(HNSW_ERR_CUDA, "speculative builder made no progress at node %u (reason %u)", f, reason);
+      // an invalid head was reset by K2 and runs from scratch next round, where it cannot fail: one idle round is legal
+      if (++idle_rounds > 3) return fail(HNSW_ERR_CUDA, "speculative builder made no progress at node %u (reason %u)", f, reason);
     }
+    if (committed) idle_rounds = 0;
   }
   if (trace)
     for (auto& x : ev) cudaEventDestroy(x);

@@ -740,6 +740,9 @@ int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value) {
   } else if (n == "spec_mult") {
     if (value < 0 || value > 1000) return fail(HNSW_ERR_INVALID, "spec_mult must be 0 (default 30 = 3.0x) .. 1000");
     ix.opt_spec_mult = (uint32_t)value;
+  } else if (n == "spec_budget_us") {
+    if (value < 0 || value > 100000) return fail(HNSW_ERR_INVALID, "spec_budget_us must be 0 (never suspend; default) .. 100000");
+    ix.opt_spec_budget_us = (int)value;
   } else if (n == "spec_ahead") {
     if (value < -1 || value > 512) return fail(HNSW_ERR_INVALID, "spec_ahead must be -1 (off), 0 (default: 2 x window) .. 512");
     ix.opt_spec_ahead = (int)value;

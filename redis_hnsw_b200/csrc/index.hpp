@@ -77,6 +77,7 @@ struct Index {
   uint32_t* d_ver0 = nullptr;     // [cap_nodes] SPEC builder row stamps: 1 + id of the last insert that wrote the row
   uint32_t* d_verU = nullptr;     // [cap_upper]
   uint32_t opt_spec_window = 0;   // SPEC: fixed window size (0 = adaptive)
+  int opt_spec_budget_us = 0;     // SPEC: an execution running longer than this stops before its next re-selection and continues in the next round; 0 = never (default: no gain once the sweeps were batched, profiles/r2_spec_build.md)
   int opt_spec_ahead = 0;         // SPEC: ids behind the window in which nodes with upper levels run those levels ahead of time; 0 = 2 x window, -1 = off
   int opt_spec_validation = 0;    // SPEC: 0 / 2 = dependency-level validation (spec.cuh), 1 = row-level (the round-2 first version; kept for A/B)
   uint32_t opt_spec_mult = 0;     // SPEC: adaptive window = mult / 10 x (inserts committed per round, running mean); 0 = 30 (3.0x: best of 1.5x .. 8x at 1M nodes, profiles/r2_spec_build.md)

@@ -42,7 +42,8 @@ namespace hnsw {
 static_assert(!kLookaheadInBuilders, "search_layer2_la does not report row ids to the search hook: the SPEC read log needs them");
 
 enum SpecHdr : int {
-  kSpecState = 0,     // 0 = needs execution, 1 = executed, 2 = only the levels above 0 are done (checkpoint, see K1)
+  kSpecState = 0,     // 0 = needs execution, 1 = executed, 2 = only the levels above 0 are done (checkpoint, see K1),
+                      // 3 = suspended between two re-selections of level 0 (time budget, see K1)
   kSpecSnap = 1,      // every insert with id < snap was committed when the level-0 part of the logs was made
   kSpecNode = 2,
   kSpecReads = 3,
@@ -65,7 +66,11 @@ enum SpecHdr : int {
   kSpecCpReprunes = 20,
   kSpecTSearch = 21,  // diagnostics: ns of this execution inside search_level,
   kSpecTSelect = 22,  //              ns inside the re-selections (sweep + top-m)
-  kSpecHdrWords = 24,
+  kSpecRused = 23,    // id words behind the read records  } only needed to continue a suspended execution
+  kSpecUsed = 24,     // words of the write log            }
+  kSpecSusI = 25,     // position in the selected list at which a suspended execution continues
+  kSpecSusSel = 26,   // number of selected neighbours (ssel)
+  kSpecHdrWords = 32,
 };
 constexpr uint32_t kSpecRdOverflow = 1, kSpecWrOverflow = 2, kSpecOpOverflow = 4;
 // read kinds (word y of a read record = kind | len << 3)
@@ -84,6 +89,7 @@ enum SpecCtl : int {
   kSpecError = 9,
   kSpecOpRows = 10,    // rows committed as operations on newer content (accumulates)
   kSpecPrepared = 11,  // checkpoints made behind the window (accumulates)
+  kSpecSuspended = 12, // executions stopped by the time budget (accumulates)
   kSpecCtlWords = 16,
 };
 
@@ -95,6 +101,8 @@ struct SpecArgs {
   uint32_t rcap, wcap, wmaxe;
   uint32_t rmax, ocap; // read records / operations per slot
   uint32_t fine;       // 1 = dependency-level validation (see header), 0 = row-level
+  uint32_t budget_ns;  // an execution that has run this long stops before its next re-selection and continues in the next K1 (0 = never)
+  uint32_t* ssel;      // [ring][m rounded up to 32]  selected neighbours of a suspended execution
   uint32_t* hdr;       // [ring][kSpecHdrWords]
   uint4* rdh;          // [ring][rmax]   read records {row key, kind | len << 3, query node | base length, threshold | growth}
   uint32_t* rdo;       // [ring][rmax]   offset of the record's ids in rd
@@ -318,16 +326,94 @@ __device__ __forceinline__ void reprune_select2v(const Graph& g, SpecLog& lg, Wa
   };
   for (uint32_t i = 0; i < n_old; i += 32) feed((i + lane < n_old) ? old[i + lane] : kEmpty);   // core.rs:549-557
   const uint32_t first_sweep = lg.n_reads;
-  for (uint32_t j = 0; j < n_old; ++j) {                         // extend_candidates (core.rs:698-721)
-    const uint32_t n_row = view_load(g, lg, old[j], level, tmp, lcap, lane);
-    // what the sweep depends on is the row in the GRAPH (the insert's own edits on top of it are the same in any order);
-    // the new node's own rows have no earlier writer
-    if (lg.fine && old[j] != lg.self) lg.read_row(g, old[j], level, row_key(g, old[j], level), kRdSweep, e, 0.f, lane);
-    if (n_row == kEmpty) {
-      if (lane == 0) atomicOr(reinterpret_cast<unsigned int*>(g.meta + kMetaError), (unsigned int)kErrListTooLong);
-      continue;
+  // extend_candidates (core.rs:698-721): the rows of the old neighbours, in order.  A row comes from the insert's own write
+  // log when it has an entry there, else from the graph.  The lookups are done for 32 rows at once (one lane per row) and
+  // the first 32 ids of 8 rows are loaded back to back, so that the sweep waits for memory once per 8 rows, not per row
+  // (measured before: ~110 us per re-selection, most of it 33 dependent row reads).
+  uint32_t* s_key = tmp + 256;                                    // per row of the group of 32: key (kEmpty = the node has no
+  uint32_t* s_ent = tmp + 288;                                    // row at this level, core.rs:642), log entry or kEmpty,
+  uint32_t* s_len = tmp + 320;                                    // length and offset of the entry's content
+  uint32_t* s_off = tmp + 352;
+  for (uint32_t j0 = 0; j0 < n_old; j0 += 32) {
+    {
+      const uint32_t id_l = j0 + lane < n_old ? old[j0 + lane] : kEmpty;
+      uint32_t key_l = kEmpty, len_l = 0, off_l = 0, ent_l = kEmpty;
+      if (id_l != kEmpty && !(level != 0 && (g.upper_base[id_l] == kEmpty || (int32_t)level > g.level[id_l]))) {
+        key_l = row_key(g, id_l, level);
+        for (uint32_t i = 0; i < lg.n_entries; ++i)
+          if (lg.wkey_s[i] == key_l) ent_l = i;                   // (superseded entries hold kEmpty)
+        if (ent_l != kEmpty) off_l = lg.woff_s[ent_l], len_l = lg.wdata[off_l + 1];
+      }
+      __syncwarp();
+      s_key[lane] = key_l, s_ent[lane] = ent_l, s_len[lane] = len_l, s_off[lane] = off_l;
+      __syncwarp();
     }
-    for (uint32_t i = 0; i < n_row; i += 32) feed((i + lane < n_row) ? tmp[i + lane] : kEmpty);
+    const uint32_t nrows = min(32u, n_old - j0);
+    for (uint32_t r0 = 0; r0 < nrows; r0 += 8) {
+      {
+        uint32_t nb8[8];                                          // 8 independent loads in flight, then parked in `tmp`
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const uint32_t src = min(r0 + r, 31u);
+          const uint32_t key = s_key[src];
+          nb8[r] = kEmpty;
+          if (r0 + r < nrows && key != kEmpty) {
+            if (s_ent[src] != kEmpty) {
+              if ((uint32_t)lane < s_len[src]) nb8[r] = lg.wdata[s_off[src] + 2 + lane];
+            } else {
+              const uint32_t* row = (key & 0x80000000u) ? g.adjU + (size_t)(key & 0x7FFFFFFFu) * g.W : g.adj0 + (size_t)key * g.W;
+              nb8[r] = __ldcg(row + lane);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) tmp[r * 32 + lane] = nb8[r];
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (uint32_t r = 0; r < 8 && r0 + r < nrows; ++r) {
+        const uint32_t src = r0 + r;
+        const uint32_t key = s_key[src];
+        if (key == kEmpty) continue;
+        const uint32_t id = old[j0 + src];
+        // what the sweep depends on is the row in the GRAPH (the insert's own edits on top of it are the same in any
+        // order); the new node's own rows have no earlier writer
+        const bool log_it = lg.fine && id != lg.self;
+        if (s_ent[src] != kEmpty) {
+          const uint32_t len = s_len[src], off = s_off[src];
+          if (log_it) lg.read_row(g, id, level, key, kRdSweep, e, 0.f, lane);
+          feed(tmp[r * 32 + lane]);
+          for (uint32_t c = 32; c < len; c += 32) feed(c + lane < len ? lg.wdata[off + 2 + c + lane] : kEmpty);
+          continue;
+        }
+        if (!lg.fine) lg.read_plain(key, kRdStrict, 0, 0, lane);
+        const uint32_t* row = (key & 0x80000000u) ? g.adjU + (size_t)(key & 0x7FFFFFFFu) * g.W : g.adj0 + (size_t)key * g.W;
+        const uint32_t* ovf = (key & 0x80000000u) ? g.ovfU + (key & 0x7FFFFFFFu) : g.ovf0 + key;
+        if (log_it) lg.begin(key, kRdSweep, e, 0.f);
+        uint32_t nb = tmp[r * 32 + lane];
+        bool more = __shfl_sync(kFull, nb, 31) != kEmpty;         // rows are compact: an empty tail ends the list
+        if (log_it) lg.ids(nb, lane);
+        feed(nb);
+        for (uint32_t c = 1; c < g.W / 32 && more; ++c) {
+          nb = __ldcg(row + c * 32 + lane);
+          more = __shfl_sync(kFull, nb, 31) != kEmpty;
+          if (log_it) lg.ids(nb, lane);
+          feed(nb);
+        }
+        uint32_t link = more ? __ldcg(ovf) : kEmpty;
+        while (link != kEmpty) {                                  // overflow rows: as list_load walks them
+          nb = __ldcg(g.pool + (size_t)link * 32 + lane);
+          const uint32_t next = __shfl_sync(kFull, nb, 31);
+          if (lane >= kPoolIds) nb = kEmpty;
+          const uint32_t n_valid = __popc(__ballot_sync(kFull, nb != kEmpty));
+          if (log_it) lg.ids(nb, lane);
+          feed(nb);
+          link = n_valid == (uint32_t)kPoolIds ? next : kEmpty;
+        }
+        if (log_it) lg.end(lane);
+      }
+      __syncwarp();
+    }
   }
   if (np) flush(np);
   L.finish(lane);                                                // wide lists (EFR >= 4): back to the sorted layout
@@ -412,8 +498,11 @@ __device__ __forceinline__ uint32_t spec_snap_of(uint32_t key, uint32_t snap0, u
 
 // One warp walks the read records lo + first, lo + first + step, ... < hi of a slot (32 at a time); true (warp-uniform) =
 // a dependency was lost.
+// `floor`: writes by inserts below it are known to be harmless (K2: the K1 of the same round checked every slot against
+// everything committed before the round).
 __device__ __forceinline__ bool spec_reads_conflict(const Graph& g, const SpecArgs& a, uint32_t slot, uint32_t snap0, uint32_t snapU,
-                                                    uint32_t lo, uint32_t hi, uint32_t first, uint32_t step, uint32_t* buf, int lane) {
+                                                    uint32_t lo, uint32_t hi, uint32_t first, uint32_t step, uint32_t* buf, int lane,
+                                                    uint32_t floor = 0) {
   const uint4* rdh = a.rdh + (size_t)slot * a.rmax;
   const uint32_t* rdo = a.rdo + (size_t)slot * a.rmax;
   const uint32_t* rd = a.rd + (size_t)slot * a.rcap;
@@ -424,7 +513,7 @@ __device__ __forceinline__ bool spec_reads_conflict(const Graph& g, const SpecAr
     if (i + lane < hi) {
       h = __ldcg(rdh + i + lane);
       off = __ldcg(rdo + i + lane);
-      stale = spec_ver(a, h.x) > spec_snap_of(h.x, snap0, snapU);
+      stale = spec_ver(a, h.x) > max(spec_snap_of(h.x, snap0, snapU), floor);
     }
     if (__any_sync(kFull, stale && ((h.y & 7u) == kRdStrict || !a.fine))) return true;
     uint32_t mask = __ballot_sync(kFull, stale);
@@ -441,7 +530,7 @@ __device__ __forceinline__ bool spec_reads_conflict(const Graph& g, const SpecAr
 // ---------------------------------------------------------------- K1
 
 template <int EFR, int C, bool SMALL>
-__global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
+__global__ void __launch_bounds__(32, 1) spec_exec_kernel(Graph g, SpecArgs a) {
   constexpr int ER = SMALL ? (EFR < 2 ? EFR : 2) : EFR;
   constexpr int S = ExactStage<C>::S;
   using T = uint32_t;
@@ -478,30 +567,41 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   if (far && l == 0) return;
   const uint32_t state = __ldcg(hdr + kSpecState);
   bool resume = false;                                            // the part above level 0 is done and still valid
-  uint32_t snapU = a.frontier;
-  if ((state == 1u || state == 2u) && __ldcg(hdr + kSpecNode) == q) {
-    const uint32_t snap0 = __ldcg(hdr + kSpecSnap), flags = __ldcg(hdr + kSpecFlags), cp_reads = __ldcg(hdr + kSpecCpReads);
+  bool relink = false;                                            // ... and so is level 0 up to a re-selection (suspended execution)
+  uint32_t snapU = a.frontier, snap0 = a.frontier;
+  if (state >= 1u && state <= 3u && __ldcg(hdr + kSpecNode) == q) {
+    const uint32_t old_snap0 = __ldcg(hdr + kSpecSnap), flags = __ldcg(hdr + kSpecFlags), cp_reads = __ldcg(hdr + kSpecCpReads);
     const uint32_t n_reads = __ldcg(hdr + kSpecReads);
     snapU = __ldcg(hdr + kSpecSnapU);
     if (flags & kSpecWrOverflow) return;                          // unusable either way: the host runs it through EXACT
     // Warp-uniform control flow on purpose: a per-lane early exit from this loop left the warp split into groups that
     // ran the whole insert below one after the other (measured: 4.1 ms instead of 0.9 ms per execution, r2 call D).
     // A log that overflowed is only good at the head of a window, where nothing can be stale.
-    const bool whole = !(flags & (kSpecRdOverflow | kSpecOpOverflow)) || (snap0 == q && snapU == q);
-    const bool okU = whole && !spec_reads_conflict(g, a, slot, snap0, snapU, 0, cp_reads, 0, 32, tmp, lane);
+    // (Only the level-0 part can have overflowed when the two snapshots differ: a checkpoint is never taken with flags set.)
+    const bool whole = !(flags & (kSpecRdOverflow | kSpecOpOverflow)) || old_snap0 == q;
+    const bool okU = whole && !spec_reads_conflict(g, a, slot, old_snap0, snapU, 0, cp_reads, 0, 32, tmp, lane);
     if (okU && state == 2u) {
       if (far) return;                                            // prepared, still good
       resume = true;
     } else if (okU) {
-      if (!spec_reads_conflict(g, a, slot, snap0, snapU, cp_reads, n_reads, 0, 32, tmp, lane)) return;   // executed, still good
-      if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist] - hdr[kSpecCpDist]);
-      if (far) {                                                  // (a window that shrank): keep the checkpoint
-        if (lane == 0) hdr[kSpecState] = 2u;
-        return;
+      if (!spec_reads_conflict(g, a, slot, old_snap0, snapU, cp_reads, n_reads, 0, 32, tmp, lane)) {
+        if (state == 1u || far) return;                           // executed (or suspended, and not wanted yet), still good
+        resume = true;
+        // The continuation reads at today's frontier but is validated against the old snapshot: sound (a row written in
+        // between only looks stale), but a re-selected row that was written in between fails its strict check.  Fine
+        // anywhere except at the head of the window, which must commit: there level 0 starts over.
+        relink = blockIdx.x != 0;
+        if (relink) snap0 = old_snap0;                            // what was read so far was read then
+      } else {
+        if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist] - hdr[kSpecCpDist]);
+        if (far) {                                                // (a window that shrank): keep the checkpoint
+          if (lane == 0) hdr[kSpecState] = 2u;
+          return;
+        }
+        resume = true;
       }
-      resume = true;
     } else {
-      if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, state == 1u ? hdr[kSpecDist] : hdr[kSpecCpDist]);
+      if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, state == 2u ? hdr[kSpecCpDist] : hdr[kSpecDist]);
       snapU = a.frontier;
     }
     __syncwarp();
@@ -538,10 +638,16 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     cp_used = __ldcg(hdr + kSpecCpUsed), cp_ops = __ldcg(hdr + kSpecCpOps), cp_ep = __ldcg(hdr + kSpecCpEp);
     cp_dist = __ldcg(hdr + kSpecCpDist), cp_reprunes = __ldcg(hdr + kSpecCpReprunes);
     lg.n_reads = cp_reads, lg.rused = cp_rused, lg.n_entries = cp_entries, lg.used = cp_used, lg.n_ops = cp_ops;
-    for (uint32_t i = lane; i < cp_entries; i += 32)
+    ep = cp_ep, cnt.n_dist = cp_dist, n_reprunes = cp_reprunes;
+    if (relink) {                                                 // ... or to where the execution was suspended
+      lg.n_reads = __ldcg(hdr + kSpecReads), lg.rused = __ldcg(hdr + kSpecRused), lg.n_entries = __ldcg(hdr + kSpecEntries);
+      lg.used = __ldcg(hdr + kSpecUsed), lg.n_ops = __ldcg(hdr + kSpecOps);
+      cnt.n_dist = __ldcg(hdr + kSpecDist), n_reprunes = __ldcg(hdr + kSpecReprunes);
+      t_search = __ldcg(hdr + kSpecTSearch), t_select = __ldcg(hdr + kSpecTSelect);
+    }
+    for (uint32_t i = lane; i < lg.n_entries; i += 32)
       lg.wkey_s[i] = __ldcg(wkey + i), lg.woff_s[i] = __ldcg(woff + i), lg.wbase_s[i] = __ldcg(wbase + i);
     __syncwarp();
-    ep = cp_ep, cnt.n_dist = cp_dist, n_reprunes = cp_reprunes;
     lc_first = 0;
   }
   for (int lc = lc_first; lc >= 0; --lc) {
@@ -568,6 +674,13 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     }
     const bool link = lc <= l;
     const uint32_t cap = lc == 0 ? a.cap0 : a.capU;               // core.rs:560
+    uint32_t n_sel, i_first = 0;
+    if (relink) {                                                 // (lc == 0) search and connect were done before the suspension
+      n_sel = __ldcg(hdr + kSpecSusSel), i_first = __ldcg(hdr + kSpecSusI);
+      const uint32_t* ss = a.ssel + (size_t)slot * ((a.m + 31) & ~31u);
+      for (uint32_t i = lane; i < n_sel; i += 32) sel[i] = __ldcg(ss + i);
+      __syncwarp();
+    } else {
     load_q_from_slab<C, S, T>(w, g, q, lane);
     const uint64_t t_s0 = spec_now();
     if constexpr (kLookahead) search_layer2_la<EFR, C, S, T>(g, w, lb, ep, link ? (int)a.efc : 1, (uint32_t)lc, L, cnt, lane, hook);   // :513, :524
@@ -576,7 +689,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
     float s;
     L.get(0, lane, false, ep, s);                                 // :514 / :576
     if (!link) continue;
-    const uint32_t n_sel = min((uint32_t)L.len, a.m);             // core.rs:531 (build.cuh header; the host sends ef_construction < m to EXACT)
+    n_sel = min((uint32_t)L.len, a.m);                            // core.rs:531 (build.cuh header; the host sends ef_construction < m to EXACT)
 #pragma unroll
     for (int r = 0; r < EFR; ++r) {
       uint32_t e = r * 32 + lane;
@@ -599,7 +712,8 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
       }
       view_store(g, lg, r, (uint32_t)lc, edit, len, base_len, lane);
     }
-    for (uint32_t i = 0; i < n_sel; ++i) {                        // shrink connections (core.rs:540-574), nearest-first
+    }  // !relink
+    for (uint32_t i = i_first; i < n_sel; ++i) {                  // shrink connections (core.rs:540-574), nearest-first
       const uint32_t e = sel[i];
       int ent;
       const uint32_t n_old = view_load(g, lg, e, (uint32_t)lc, old, a.lcap, lane, &ent);
@@ -611,6 +725,30 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
         if (lg.fine)                                              // in the graph grows by at most cap - n_old ids
           lg.read_plain(row_key(g, e, (uint32_t)lc), kRdLenBound, ent >= 0 ? lg.wbase_s[ent] : n_old, cap - n_old, lane);
         continue;
+      }
+      // Time budget: a round lasts as long as its slowest execution, and the slow ones are the inserts with many
+      // re-selections (~0.1 ms each; 10+ happen).  Past the budget the execution stops HERE and continues in the next K1
+      // (never the head of the window: every round must be able to commit).
+      if (lc == 0 && a.budget_ns && blockIdx.x != 0 && !lg.flags && spec_now() - t_in > a.budget_ns) {
+        __syncwarp();
+        for (uint32_t k = lane; k < lg.n_entries; k += 32) wkey[k] = lg.wkey_s[k], woff[k] = lg.woff_s[k], wbase[k] = lg.wbase_s[k];
+        uint32_t* ss = a.ssel + (size_t)slot * ((a.m + 31) & ~31u);
+        for (uint32_t k = lane; k < n_sel; k += 32) ss[k] = sel[k];
+        if (lane == 0) {
+          hdr[kSpecSnap] = snap0, hdr[kSpecSnapU] = snapU, hdr[kSpecNode] = q;
+          hdr[kSpecCpReads] = cp_reads, hdr[kSpecCpRused] = cp_rused, hdr[kSpecCpEntries] = cp_entries, hdr[kSpecCpUsed] = cp_used;
+          hdr[kSpecCpOps] = cp_ops, hdr[kSpecCpEp] = cp_ep, hdr[kSpecCpDist] = cp_dist, hdr[kSpecCpReprunes] = cp_reprunes;
+          hdr[kSpecReads] = lg.n_reads, hdr[kSpecRused] = lg.rused, hdr[kSpecEntries] = lg.n_entries, hdr[kSpecUsed] = lg.used;
+          hdr[kSpecOps] = lg.n_ops, hdr[kSpecFlags] = 0, hdr[kSpecDist] = cnt.n_dist, hdr[kSpecReprunes] = n_reprunes;
+          hdr[kSpecSusI] = i, hdr[kSpecSusSel] = n_sel;
+          hdr[kSpecTSearch] = t_search, hdr[kSpecTSelect] = t_select;
+          hdr[kSpecDur] = (uint32_t)(spec_now() - t_in);
+          hdr[kSpecSm] = smid | 0x20000000u;
+          __threadfence();
+          hdr[kSpecState] = 3u;
+          atomicAdd(a.ctl + kSpecSuspended, 1u);
+        }
+        return;
       }
       if (lg.fine) lg.read_plain(row_key(g, e, (uint32_t)lc), kRdStrict, 0, 0, lane);   // re-selected: its content decides
       load_q_from_slab<C, S, T>(w, g, e, lane);
@@ -649,7 +787,7 @@ __global__ void __launch_bounds__(32) spec_exec_kernel(Graph g, SpecArgs a) {
   __syncwarp();
   for (uint32_t i = lane; i < lg.n_entries; i += 32) wkey[i] = lg.wkey_s[i], woff[i] = lg.woff_s[i], wbase[i] = lg.wbase_s[i];
   if (lane == 0) {
-    hdr[kSpecSnap] = a.frontier;
+    hdr[kSpecSnap] = snap0;
     hdr[kSpecSnapU] = snapU;
     hdr[kSpecNode] = q;
     hdr[kSpecCpReads] = cp_reads, hdr[kSpecCpRused] = cp_rused, hdr[kSpecCpEntries] = cp_entries, hdr[kSpecCpUsed] = cp_used;
@@ -703,8 +841,8 @@ __global__ void __launch_bounds__(512) spec_commit_kernel(Graph g, SpecArgs a) {
     const uint32_t* wdata = a.wdata + (size_t)slot * a.wcap;
     // valid iff nothing the insert depended on was written after its snapshot (the warps share the read records)
     // (a log that overflowed is only good at the head of a window, where nothing can be stale)
-    int bad = ((flags & (kSpecRdOverflow | kSpecOpOverflow)) && !(snap == q && snapU == q)) ? 1 : 0;
-    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, snapU, 0, n_reads, (uint32_t)warp * 32, (uint32_t)warps * 32, buf, lane) ? 1 : 0;
+    int bad = ((flags & (kSpecRdOverflow | kSpecOpOverflow)) && snap != q) ? 1 : 0;
+    if (!bad) bad = spec_reads_conflict(g, a, slot, snap, snapU, 0, n_reads, (uint32_t)warp * 32, (uint32_t)warps * 32, buf, lane, a.frontier) ? 1 : 0;
     // overflow rows the commit can allocate at most (chains already in place are not counted: an upper bound; a row that
     // takes operations instead of content grows by a few ids over what it holds)
     uint32_t need = 0;

@@ -81,6 +81,47 @@ def test_spec_graph_does_not_depend_on_the_window():
     _assert_same_graph(d2.export_graph(), dev.export_graph())
 
 
+@pytest.mark.parametrize("options", [
+    {"spec_validation": 1},                        # row-level validation (the first version of round 2)
+    {"spec_ahead": -1},                            # no checkpoints ahead of the window
+    {"spec_ahead": 500, "spec_window": 16},        # ... and far more of them than windows
+    {"spec_budget_us": 300},                       # nearly every execution is suspended and continued
+    {"spec_budget_us": 600, "spec_window": 64},
+    {"spec_mult": 100},                            # windows of 10 x the commit rate: most executions are thrown away
+])
+def test_spec_graph_does_not_depend_on_the_policy(options):
+    """Validation level, checkpoints ahead of the window and the time budget change WHEN an insert is executed and how
+    often, never what is committed."""
+    import redis_hnsw_b200 as r
+
+    c = case("d128_m16")
+    n = 5000
+    x, levels = c["x"][:n], c["levels"][:n]
+    orc = oracle.Oracle(c["dim"], c["m"], c["efc"])
+    orc.add_batch(x, levels)
+    dev = r.DeviceIndex(c["dim"], c["m"], c["efc"])
+    for k, v in options.items():
+        dev.set_option(k, v)
+    dev.add_batch(x, levels, mode=r.BUILD_SPEC)
+    _assert_same_graph(dev.export_graph(), orc.export_graph(), x=x)
+
+
+def test_spec_long_rows_with_a_time_budget():
+    """768-d, M=32: rows of 64 ids, read logs that overflow (such an insert is only good at the head of a window) and
+    executions slower than the budget — the combination that once left a round without a commit."""
+    import redis_hnsw_b200 as r
+
+    c = case("d768_m32")
+    n = 1200
+    x, levels = c["x"][:n], c["levels"][:n]
+    orc = oracle.Oracle(c["dim"], c["m"], c["efc"])
+    orc.add_batch(x, levels)
+    dev = r.DeviceIndex(c["dim"], c["m"], c["efc"])
+    dev.set_option("spec_budget_us", 1300)
+    dev.add_batch(x, levels, mode=r.BUILD_SPEC)
+    _assert_same_graph(dev.export_graph(), orc.export_graph(), x=x)
+
+
 def test_spec_in_pieces_then_single_adds_and_deletes():
     """SPEC streams appended to an existing graph, mixed with NODE.ADD / NODE.DEL one at a time: still the oracle's graph
     (row stamps of earlier calls must not confuse later ones)."""

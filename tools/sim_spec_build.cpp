@@ -280,6 +280,7 @@ static int verify(size_t n, const std::vector<size_t>& cps, int B) {
               (void)n_added;
             }
             if (fine_hit) conflict[1] = true;
+            if (op_hit && !conflict[2]) ++KH[rd.kind & 7];
             if (op_hit) conflict[2] = true;
           }
         // what did the two executions write?
@@ -322,6 +323,9 @@ static int verify(size_t n, const std::vector<size_t>& cps, int B) {
       }
       for (int c = 0; c < 3; ++c) prefix_sum[c] += pre[c];
     }
+    printf("   first conflicting read of fine+oplog by kind: strict %llu search %llu sweep %llu lenbound %llu\n", (unsigned long long)KH[0],
+           (unsigned long long)KH[1], (unsigned long long)KH[2], (unsigned long long)KH[6]);
+    for (auto& k : KH) k = 0;
     printf("N=%zu B=%d inserts=%zu | accepted coarse %zu fine %zu fine+oplog %zu | violations %zu %zu %zu | mean prefix %.1f %.1f %.1f\n", cp, B,
            total, accepted[0], accepted[1], accepted[2], violations[0], violations[1], violations[2], (double)prefix_sum[0] / windows,
            (double)prefix_sum[1] / windows, (double)prefix_sum[2] / windows);
