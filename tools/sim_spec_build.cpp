@@ -73,7 +73,10 @@ static uint32_t epoch = 0;
 
 typedef std::pair<float, uint32_t> P;
 
+static bool RETRO = false;   // SIM_RETRO=1: search reads get the retroactive threshold (see search_level)
 static std::vector<P> search_level(uint32_t q, uint32_t ep, int ef, int lvl) {
+  const size_t first_read = LOG ? LOG->reads.size() : 0;
+  std::vector<float> csim;                                        // sim of the candidate whose row read i is
   ++epoch;
   stamp[ep] = epoch;
   std::priority_queue<P> c;                                      // nearest first
@@ -87,7 +90,7 @@ static std::vector<P> search_level(uint32_t q, uint32_t ep, int ef, int lvl) {
     if (cp.first < w.top().first) break;
     const auto& nb = NB[cp.second];
     if ((int)nb.size() <= lvl) continue;
-    if (LOG) LOG->reads.push_back({key(cp.second, lvl), 1, q, (int)w.size() >= ef ? w.top().first : -INFINITY});
+    if (LOG) LOG->reads.push_back({key(cp.second, lvl), 1, q, (int)w.size() >= ef ? w.top().first : -INFINITY}), csim.push_back(cp.first);
     for (uint32_t n : nb[lvl]) {
       if (stamp[n] == epoch) continue;
       stamp[n] = epoch;
@@ -97,6 +100,18 @@ static std::vector<P> search_level(uint32_t q, uint32_t ep, int ef, int lvl) {
         w.push({e, n});
         if ((int)w.size() > ef) w.pop();
       }
+    }
+  }
+  // Retroactive threshold: an id that shows up in (or vanishes from) the row of read i is harmless when it is farther than
+  // every candidate expanded AFTER read i and farther than the final worst of a full list: it would sit in the list for
+  // a while, never be the nearest unexpanded candidate, and be gone at the end; everything nearer evolves the same.
+  if (LOG && RETRO && (int)w.size() >= ef) {
+    float t = w.top().first;
+    for (size_t i = csim.size(); i-- > 0;) {
+      Read& rd = LOG->reads[first_read + i];
+      const float below = std::nextafter(t, -INFINITY);
+      if (below > rd.thr) rd.thr = below;
+      t = std::min(t, csim[i]);
     }
   }
   std::vector<P> out;
@@ -466,6 +481,7 @@ int main(int argc, char** argv) {
   }
   LEVEL[0] = 0;
   NB.resize(n);
+  RETRO = getenv("SIM_RETRO") != nullptr;
   if (getenv("SIM_PIPE")) return pipe_sim(n, cps);
   if (getenv("SIM_VERIFY")) return verify(n, cps, atoi(getenv("SIM_VERIFY")));
   stamp.assign(n, 0);
