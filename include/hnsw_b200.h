@@ -195,7 +195,13 @@ int hnsw_index_adopt_replica(hnsw_index_t* idx);
 /* Named integer options: "visited_slots" (per-query visited hash slots, power of two, 0 = auto),
  * "search_ctas_per_sm", "build_batch" (nodes per batch of the FAST builder), "build_impl" (0 auto, 1 = register-staged
  * batch searches, 2 = TMA-staged), "search_impl", "stage_rows", "recent_slots", "recent_tag", "search_block", "row_copy"
- * (1 = cp.async row staging for 32-d / 128-d rows, the default; 0 = bulk-async copies for every dimension).
+ * (1 = cp.async row staging for 32-d / 128-d rows, the default; 0 = bulk-async copies for every dimension),
+ * "recent_ways" (1 | 2), "lookahead" (0 | 1), "search_cta" (0 | 1: one query per CTA of four warps for small calls).
+ * SPEC builder (HNSW_BUILD_SPEC; none of these changes the graph, tests/test_gpu_spec_build.py): "spec_window" (fixed
+ * window, 0 = adaptive), "spec_mult" (adaptive window = value / 10 x inserts committed per round; 0 = 30),
+ * "spec_validation" (0 | 2 = dependency-level, 1 = row-level), "spec_ahead" (ids behind the window in which nodes with
+ * upper levels run those levels ahead of time; 0 = 2 x window, -1 = off), "spec_budget_us" (an execution running longer
+ * stops before its next re-selection and continues in the next round; 0 = never).
  * Unknown names -> HNSW_ERR_INVALID. */
 int hnsw_index_set_option(hnsw_index_t* idx, const char* name, int64_t value);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */

@@ -591,6 +591,18 @@ __global__ void __launch_bounds__(32, 1) spec_exec_kernel(Graph g, SpecArgs a) {
         // between only looks stale), but a re-selected row that was written in between fails its strict check.  Fine
         // anywhere except at the head of the window, which must commit: there level 0 starts over.
         relink = blockIdx.x != 0;
+        // The continuation reads its own write log, whose rows were derived from the graph as it stood at the old
+        // snapshot, AND the graph as it stands now (where a sweep logs "the row in the graph" for a row it took from its
+        // log, reprune_select2v): the two must be the same rows.  If any row under the write log was written since, level
+        // 0 starts over.  (Found by synccheck's timing: a budget of 150 us on 32-d data committed a different graph.)
+        if (relink) {
+          const uint32_t n_e = __ldcg(hdr + kSpecEntries);
+          const uint32_t* wk = a.wkey + (size_t)slot * a.wmaxe;
+          for (uint32_t i = 0; i < n_e && relink; i += 32) {
+            const uint32_t key = i + lane < n_e ? __ldcg(wk + i + lane) : kEmpty;
+            relink = !__any_sync(kFull, key != kEmpty && spec_ver(a, key) > spec_snap_of(key, old_snap0, snapU));
+          }
+        }
         if (relink) snap0 = old_snap0;                            // what was read so far was read then
       } else {
         if (lane == 0) atomicAdd(a.ctl + kSpecDistWasted, hdr[kSpecDist] - hdr[kSpecCpDist]);
