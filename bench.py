@@ -410,7 +410,9 @@ def main():
     nq_total = args.nq if strong else args.nq * eff_world
     n_probe = 2000
     t_setup = time.perf_counter()
-    n_q = max(nq_total, 10_000) + n_probe
+    # the query stream is generated for the N the command names, in both arms: the reference arm (rank 0 only) then sees
+    # the queries — and reports the recall and `config` — of the arm it is compared with
+    n_q = max(args.nq if strong else args.nq * world, 10_000) + n_probe
     if rank == 0 or ref_arm:
         x, q_all, levels = make_data(wl, n_q)
     else:                                 # only the builder needs the vectors: the other ranks receive the index over NCCL
@@ -452,7 +454,7 @@ def main():
                 "graph": GRAPH_LABEL[args.graph], "graph_builder": args.graph,
                 "l2_policy": "inputs larger than L2 (vector slab %d MB + adjacency; L2 126 MB), no flush" % (n * dim * 4 >> 20)}
     if strong:
-        base_cfg.update(batch_queries=nq_total, queries_per_gpu=nq_total // eff_world,
+        base_cfg.update(batch_queries=nq_total, queries_per_gpu=nq_total // world,
                         step_is="one %d-query batch sliced over the GPUs + all-gather of the result slices" % nq_total)
     else:
         base_cfg.update(queries_per_gpu_per_step=args.nq)
