@@ -12,6 +12,16 @@
 // Output per window size B: inserts with at least one dependency, longest chain (= Jacobi sweeps needed), length of
 // the conflict-free prefix.
 //
+// Modes (environment):
+//   (none)          dependency statistics per window size, for row-level / fine / op-log validation (the original probe)
+//   SIM_VERIFY=B    SOUNDNESS of the device's validation rules (spec.cuh): every insert of a window of B is executed twice,
+//                   against the snapshot at the window start and in stream order; whenever a rule set calls the speculative
+//                   execution valid, its writes must BE the sequential ones.  Prints accepted / violations (must be 0) for
+//                   row-level | fine | fine + operations, and which read kind caused the first conflict.
+//                   SIM_WINDOWS=n windows per checkpoint.  SIM_RETRO=1 adds the retroactive search threshold (see search_level).
+//   SIM_PIPE=1      event simulation of persistent warps with a ticket and in-order self-commit (no rounds): inserts/s for
+//                   W = 8..128 warps, with and without early re-execution, row-level vs fine + operations.
+//
 // usage: sim_spec_build vecs.bin n dim m efc seed checkpoints...      (vecs.bin = raw f32 [n][dim])
 #include <algorithm>
 #include <cmath>
