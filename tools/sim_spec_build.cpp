@@ -19,6 +19,8 @@
 //                   execution valid, its writes must BE the sequential ones.  Prints accepted / violations (must be 0) for
 //                   row-level | fine | fine + operations, and which read kind caused the first conflict.
 //                   SIM_WINDOWS=n windows per checkpoint.  SIM_RETRO=1 adds the retroactive search threshold (see search_level).
+//                   SIM_UNSOUND=1 drops the strict-read rule from the third rule set: the replay must then find violations
+//                   (tests/test_spec_rules_cpu.py uses it as the negative control).
 //   SIM_PIPE=1      event simulation of persistent warps with a ticket and in-order self-commit (no rounds): inserts/s for
 //                   W = 8..128 warps, with and without early re-execution, row-level vs fine + operations.
 //
@@ -304,6 +306,7 @@ static int verify(size_t n, const std::vector<size_t>& cps, int B) {
               op_hit = true_len > (size_t)rd.qnode + (size_t)rd.thr;
               (void)n_added;
             }
+            if (getenv("SIM_UNSOUND") && rd.kind == 0) op_hit = false;   // negative control: drop the strict rule
             if (fine_hit) conflict[1] = true;
             if (op_hit && !conflict[2]) ++KH[rd.kind & 7];
             if (op_hit) conflict[2] = true;
