@@ -582,11 +582,12 @@ void cmd_msearch(RedisModuleCtx* ctx, const std::vector<std::string>& args) {
 }
 
 // extension: HNSW.NODE.MADD {index} [FAST 0|1] NODES {n} {name1..namen} DATA {n} {dim} {n*dim values}
-// a NODE.ADD stream in one command (bulk load); FAST 1 (default) uses the batched device builder, FAST 0 the
-// sequentially consistent one.  Replies the number of nodes added.
+// a NODE.ADD stream in one command (bulk load).  FAST 0 (default) builds exactly the graph the same stream of NODE.ADD
+// commands builds (the device's speculative-exact builder, csrc/spec.cuh); FAST 1 uses the batched builder, whose graph
+// has the same quality but is not the reference's.  Replies the number of nodes added.
 void cmd_node_madd(RedisModuleCtx* ctx, const std::vector<std::string>& args) {
   Parsed p = parse_args(args, "hnsw.node.madd", 1,
-                        {{"FAST", kU64, false, 1}, {"NODES", kStrVec, true, 0}, {"DATA", kF64Vec, true, 0}}, "DATA");
+                        {{"FAST", kU64, false, 0}, {"NODES", kStrVec, true, 0}, {"DATA", kF64Vec, true, 0}}, "DATA");
   const std::string index_name = std::string(PREFIX) + "." + p.pos[0];
   const std::vector<std::string>& suffixes = p.strs["NODES"];
   if (p.vec_rows["DATA"] != suffixes.size()) throw ReplyError{"ERR NODES and DATA announce different counts"};
