@@ -87,3 +87,38 @@ def test_oracle_on_the_exported_graph_matches(big):
     oids2, osims2, _, ost2, _ = orc.search_batch(q[:500], K, threads=8)
     ok2 = ost2[:, 3] == 0
     assert np.array_equal(ids2[ok2], oids2[ok2]) and np.array_equal(sims2[ok2].view(np.uint32), osims2[ok2].view(np.uint32))
+
+
+def test_exact_and_spec_inserts_at_full_size(big):
+    """NODE.ADD on the 1M-node graph (core.rs:489-599): one command at a time through the one-warp EXACT kernel, then a
+    stream through the SPEC builder — both must leave the lists the oracle's insert leaves, for the new nodes and for the
+    old nodes they were linked to.  (Runs last: it grows the index.)"""
+    import oracle
+    import redis_hnsw_b200 as r
+    from redis_hnsw_b200 import data
+
+    dev, x, q = big["dev"], big["x"], big["q"]
+    orc = oracle.Oracle(DIM, M, EFC)
+    orc.import_graph(x, dev.export_graph())
+    n_single, n_stream = 60, 400
+    new = q[12_000:12_000 + n_single + n_stream]                   # same distribution as the data (same generator stream)
+    lv = data.draw_levels(n_single + n_stream, M, seed=4242)
+    for i in range(n_single):
+        assert dev.add(new[i], int(lv[i])) == orc.add(new[i], int(lv[i])) == N + i
+    orc.add_batch(new[n_single:], lv[n_single:])
+    assert dev.add_batch(new[n_single:], lv[n_single:], mode=r.BUILD_SPEC) == N + n_single
+    st = dev.build_stats()
+    assert st["spec_rounds"] > 0 and st["spec_rounds"] < n_stream  # windows did commit more than one insert per round
+    p, op = dev.params(), orc.params()
+    for key in ("node_count", "max_layer", "enterpoint"):
+        assert p[key] == op[key], key
+    touched = set()
+    for j in range(N, N + n_single + n_stream):
+        assert dev.node_level(j) == int(lv[j - N])
+        for level in range(int(lv[j - N]) + 1):
+            nb = dev.node_neighbors(j, level)
+            assert np.array_equal(nb, orc.node_neighbors(j, level)), (j, level)
+            if level == 0:
+                touched.update(int(v) for v in nb)
+    for v in sorted(touched)[:3000]:                               # old rows that got a new neighbour (and maybe a re-selection)
+        assert np.array_equal(dev.node_neighbors(v, 0), orc.node_neighbors(v, 0)), v
