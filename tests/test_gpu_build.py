@@ -184,6 +184,9 @@ def test_fast_build_invariants_recall_and_tier2_parity(name, n, batch):
     if batch:
         dev.set_option("build_batch", batch)
     dev.add_batch(x, levels, mode=r.BUILD_FAST)
+    st = dev.build_stats()
+    # the batched builder's lossy valves (worklist full, re-selection skipped, hub row full) must stay shut here
+    assert (st["fast_worklist_dropped"], st["fast_reprunes_skipped"], st["fast_edges_refused"]) == (0, 0, 0), st
     g = dev.export_graph()
     assert np.array_equal(g["levels"], levels.clip(min=0) * (np.arange(n) > 0))  # first node sits on level 0
     over = _check_invariants(g, c["m"])

@@ -26,6 +26,8 @@ def test_params_and_structure(big):
     dev, levels = big["dev"], big["levels"]
     p = dev.params()
     assert p["node_count"] == N and p["n_ids"] == N and p["m_max_0"] == 2 * M
+    st = dev.build_stats()                                         # the FAST builder dropped nothing on the headline workload
+    assert (st["fast_worklist_dropped"], st["fast_reprunes_skipped"], st["fast_edges_refused"]) == (0, 0, 0), st
     top = int(levels[1:].max())                                    # the first node is forced to level 0 (core.rs:393-405)
     assert p["max_layer"] == top and dev.node_level(p["enterpoint"]) == top   # core.rs:587-593
     rng = np.random.default_rng(0)
