@@ -23,6 +23,7 @@
 //                   (tests/test_spec_rules_cpu.py uses it as the negative control).
 //   SIM_PIPE=1      event simulation of persistent warps with a ticket and in-order self-commit (no rounds): inserts/s for
 //                   W = 8..128 warps, with and without early re-execution, row-level vs fine + operations.
+//                   SIM_PIPE_COMMIT_US=c cost of one commit (default 15), SIM_PIPE_QUICK=1 only the interesting corner.
 //
 // usage: sim_spec_build vecs.bin n dim m efc seed checkpoints...      (vecs.bin = raw f32 [n][dim])
 #include <algorithm>
@@ -407,13 +408,15 @@ static int pipe_sim(size_t n, const std::vector<size_t>& cps) {
   stamp.assign(n, 0);
   NB[0].resize(1);
   size_t next = 1;
-  const double Tbase = 0.9e-3, c_commit = 15e-6;
+  const double Tbase = 0.9e-3, c_commit = (getenv("SIM_PIPE_COMMIT_US") ? atof(getenv("SIM_PIPE_COMMIT_US")) : 15.0) * 1e-6;
+  const bool quick = getenv("SIM_PIPE_QUICK") != nullptr;   // only fine + operations with early re-execution, W = 16..64
   const int per_cfg = getenv("SIM_PIPE_N") ? atoi(getenv("SIM_PIPE_N")) : 1500;
   for (size_t cp : cps) {
     for (; next < cp && next < n; ++next) insert((uint32_t)next);
     for (int crit : {0, 2})
       for (int early : {0, 1})
         for (int W : {8, 16, 32, 64, 128}) {
+          if (quick && (W < 16 || W > 64 || crit != 2 || early != 1)) continue;
           if (next + per_cfg + 200 >= n) return 0;
           const size_t first = next, last = next + per_cfg;
           std::vector<Flight*> fl;          // in flight, ordered by q
